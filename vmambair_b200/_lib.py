@@ -1,0 +1,73 @@
+"""ctypes loader of the C-ABI library (include/vmambair_b200.h).
+
+There is NO fallback: if the CUDA library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvmambair_b200.so")
+_lib = None
+
+DT_F32, DT_BF16, DT_F16 = 0, 1, 2
+
+i64 = C.c_int64
+vp = C.c_void_p
+
+
+class ScanFwdArgs(C.Structure):
+    _fields_ = [
+        ("u", vp), ("delta", vp), ("A", vp), ("Bm", vp), ("Cm", vp), ("D", vp), ("delta_bias", vp),
+        ("out", vp), ("ckpt", vp),
+        ("batch", C.c_int), ("dim", C.c_int), ("seqlen", C.c_int), ("dstate", C.c_int), ("ngroups", C.c_int),
+        ("u_bs", i64), ("u_ds", i64), ("delta_bs", i64), ("delta_ds", i64), ("out_bs", i64), ("out_ds", i64),
+        ("B_bs", i64), ("B_gs", i64), ("B_ns", i64), ("C_bs", i64), ("C_gs", i64), ("C_ns", i64),
+        ("delta_softplus", C.c_int), ("dtype", C.c_int),
+    ]
+
+
+class ScanBwdArgs(C.Structure):
+    _fields_ = [
+        ("u", vp), ("delta", vp), ("A", vp), ("Bm", vp), ("Cm", vp), ("D", vp), ("delta_bias", vp),
+        ("dout", vp), ("ckpt", vp),
+        ("du", vp), ("ddelta", vp), ("dA", vp), ("dB", vp), ("dC", vp), ("dD", vp), ("ddelta_bias", vp),
+        ("batch", C.c_int), ("dim", C.c_int), ("seqlen", C.c_int), ("dstate", C.c_int), ("ngroups", C.c_int),
+        ("u_bs", i64), ("u_ds", i64), ("delta_bs", i64), ("delta_ds", i64), ("dout_bs", i64), ("dout_ds", i64),
+        ("du_bs", i64), ("du_ds", i64), ("ddelta_bs", i64), ("ddelta_ds", i64),
+        ("B_bs", i64), ("B_gs", i64), ("B_ns", i64), ("C_bs", i64), ("C_gs", i64), ("C_ns", i64),
+        ("delta_softplus", C.c_int), ("dtype", C.c_int),
+    ]
+
+
+# every symbol include/vmambair_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "vmb_last_error": (C.c_char_p, []),
+    "vmb_version": (C.c_char_p, []),
+    "vmb_scan_ckpt_interval": (C.c_int, []),
+    "vmb_selective_scan_fwd": (C.c_int, [C.POINTER(ScanFwdArgs), vp]),
+    "vmb_selective_scan_bwd": (C.c_int, [C.POINTER(ScanBwdArgs), vp]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"vmambair_b200: CUDA library not built ({LIB_PATH}); run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C vmambair_b200/csrc`. There is no CPU fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)  # AttributeError if the .so does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        msg = lib().vmb_last_error().decode()
+        raise RuntimeError(f"{what}: {msg} (status {status})")

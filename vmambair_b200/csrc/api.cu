@@ -1,0 +1,91 @@
+// C-ABI entry points (include/vmambair_b200.h): argument validation + launch.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "scan_params.h"
+
+namespace vmb {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+static inline int elt_size(int dtype) { return dtype == VMB_F32 ? 4 : 2; }
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+}  // namespace vmb
+
+using namespace vmb;
+
+extern "C" const char* vmb_last_error(void) { return g_err; }
+extern "C" const char* vmb_version(void) { return "vmambair_b200 0.1 sm_100a"; }
+extern "C" int vmb_scan_ckpt_interval(void) { return kScanCkpt; }
+
+extern "C" int vmb_selective_scan_fwd(const vmb_scan_fwd_args* a, void* stream) {
+    VMB_CHECK(a != nullptr, "selective_scan_fwd: null args");
+    VMB_CHECK(a->dtype == VMB_F32 || a->dtype == VMB_BF16 || a->dtype == VMB_F16,
+              "selective_scan_fwd: dtype must be f32/bf16/f16 (got %d)", a->dtype);
+    VMB_CHECK(a->u && a->delta && a->A && a->Bm && a->Cm && a->out, "selective_scan_fwd: null tensor pointer");
+    VMB_CHECK(a->batch > 0 && a->dim > 0 && a->seqlen > 0 && a->dstate > 0 && a->ngroups > 0,
+              "selective_scan_fwd: non-positive size");
+    VMB_CHECK(a->dim % a->ngroups == 0, "selective_scan_fwd: dims should be dividable by n_groups");
+    VMB_CHECK(a->dstate <= 256, "selective_scan only supports state dimension <= 256");
+    VMB_CHECK(a->batch <= 65535, "selective_scan_fwd: batch > 65535");
+    ScanFwdParams p{};
+    p.u = a->u; p.delta = a->delta; p.Bm = a->Bm; p.Cm = a->Cm; p.A = a->A; p.D = a->D; p.bias = a->delta_bias;
+    p.out = a->out; p.ckpt = a->ckpt;
+    p.batch = a->batch; p.dim = a->dim; p.L = a->seqlen; p.N = a->dstate; p.G = a->ngroups;
+    p.npad = (a->dstate + 15) / 16 * 16;
+    p.rows_per_group = a->dim / a->ngroups;
+    p.n_ckpt = (a->seqlen + kScanCkpt - 1) / kScanCkpt;
+    p.u_bs = a->u_bs; p.u_ds = a->u_ds; p.dl_bs = a->delta_bs; p.dl_ds = a->delta_ds; p.o_bs = a->out_bs; p.o_ds = a->out_ds;
+    p.B_bs = a->B_bs; p.B_gs = a->B_gs; p.B_ns = a->B_ns; p.C_bs = a->C_bs; p.C_gs = a->C_gs; p.C_ns = a->C_ns;
+    p.softplus = a->delta_softplus;
+    const int v = 16 / elt_size(a->dtype);
+    auto mult = [v](int64_t s) { return s % v == 0; };
+    p.vec_ok = aligned16(a->u) && aligned16(a->delta) && aligned16(a->Bm) && aligned16(a->Cm) && aligned16(a->out) &&
+               mult(a->u_bs) && mult(a->u_ds) && mult(a->delta_bs) && mult(a->delta_ds) && mult(a->out_bs) &&
+               mult(a->out_ds) && mult(a->B_bs) && mult(a->B_gs) && mult(a->B_ns) && mult(a->C_bs) && mult(a->C_gs) &&
+               mult(a->C_ns);
+    return scan_fwd_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vmb_selective_scan_bwd(const vmb_scan_bwd_args* a, void* stream) {
+    VMB_CHECK(a != nullptr, "selective_scan_bwd: null args");
+    VMB_CHECK(a->dtype == VMB_F32 || a->dtype == VMB_BF16 || a->dtype == VMB_F16,
+              "selective_scan_bwd: dtype must be f32/bf16/f16 (got %d)", a->dtype);
+    VMB_CHECK(a->u && a->delta && a->A && a->Bm && a->Cm && a->dout && a->du && a->ddelta && a->dA && a->dB && a->dC,
+              "selective_scan_bwd: null tensor pointer");
+    VMB_CHECK(a->batch > 0 && a->dim > 0 && a->seqlen > 0 && a->dstate > 0 && a->ngroups > 0,
+              "selective_scan_bwd: non-positive size");
+    VMB_CHECK(a->dim % a->ngroups == 0, "selective_scan_bwd: dims should be dividable by n_groups");
+    VMB_CHECK(a->dstate <= 256, "selective_scan only supports state dimension <= 256");
+    VMB_CHECK(a->batch <= 65535, "selective_scan_bwd: batch > 65535");
+    VMB_CHECK(a->ckpt != nullptr || a->seqlen <= kScanCkpt,
+              "selective_scan_bwd: forward checkpoints required when seqlen > %d", kScanCkpt);
+    VMB_CHECK((a->D == nullptr) == (a->dD == nullptr), "selective_scan_bwd: D and dD must both be given or both be NULL");
+    VMB_CHECK((a->delta_bias == nullptr) == (a->ddelta_bias == nullptr),
+              "selective_scan_bwd: delta_bias and ddelta_bias must both be given or both be NULL");
+    ScanBwdParams p{};
+    p.u = a->u; p.delta = a->delta; p.Bm = a->Bm; p.Cm = a->Cm; p.dout = a->dout; p.A = a->A; p.D = a->D;
+    p.bias = a->delta_bias; p.ckpt = a->ckpt; p.du = a->du; p.ddelta = a->ddelta; p.dA = a->dA; p.dB = a->dB; p.dC = a->dC;
+    p.dD = a->dD; p.dbias = a->ddelta_bias;
+    p.batch = a->batch; p.dim = a->dim; p.L = a->seqlen; p.N = a->dstate; p.G = a->ngroups;
+    p.npad = (a->dstate + 15) / 16 * 16;
+    p.rows_per_group = a->dim / a->ngroups;
+    p.n_ckpt = (a->seqlen + kScanCkpt - 1) / kScanCkpt;
+    p.u_bs = a->u_bs; p.u_ds = a->u_ds; p.dl_bs = a->delta_bs; p.dl_ds = a->delta_ds; p.do_bs = a->dout_bs; p.do_ds = a->dout_ds;
+    p.du_bs = a->du_bs; p.du_ds = a->du_ds; p.dd_bs = a->ddelta_bs; p.dd_ds = a->ddelta_ds;
+    p.B_bs = a->B_bs; p.B_gs = a->B_gs; p.B_ns = a->B_ns; p.C_bs = a->C_bs; p.C_gs = a->C_gs; p.C_ns = a->C_ns;
+    p.softplus = a->delta_softplus;
+    const int v = 16 / elt_size(a->dtype);
+    auto mult = [v](int64_t s) { return s % v == 0; };
+    p.vec_ok = aligned16(a->u) && aligned16(a->delta) && aligned16(a->Bm) && aligned16(a->Cm) && aligned16(a->dout) &&
+               aligned16(a->du) && aligned16(a->ddelta) && mult(a->u_bs) && mult(a->u_ds) && mult(a->delta_bs) &&
+               mult(a->delta_ds) && mult(a->dout_bs) && mult(a->dout_ds) && mult(a->du_bs) && mult(a->du_ds) &&
+               mult(a->ddelta_bs) && mult(a->ddelta_ds) && mult(a->B_bs) && mult(a->B_gs) && mult(a->B_ns) &&
+               mult(a->C_bs) && mult(a->C_gs) && mult(a->C_ns);
+    return scan_bwd_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,38 @@
+// Internal parameter blocks of the selective-scan kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vmb {
+
+constexpr int kScanT = 16;      // sequence positions per lane per chunk
+constexpr int kScanCkpt = 256;  // checkpoint interval (positions); see vmb_scan_ckpt_interval()
+
+struct ScanFwdParams {
+    const void *u, *delta, *Bm, *Cm;
+    const float *A, *D, *bias;
+    void* out;
+    float* ckpt;
+    int batch, dim, L, N, G, npad, rows_per_group, n_ckpt;
+    int64_t u_bs, u_ds, dl_bs, dl_ds, o_bs, o_ds;
+    int64_t B_bs, B_gs, B_ns, C_bs, C_gs, C_ns;
+    int softplus;
+    bool vec_ok;
+};
+
+struct ScanBwdParams {
+    const void *u, *delta, *Bm, *Cm, *dout;
+    const float *A, *D, *bias, *ckpt;
+    void *du, *ddelta;
+    float *dA, *dB, *dC, *dD, *dbias;
+    int batch, dim, L, N, G, npad, rows_per_group, n_ckpt;
+    int64_t u_bs, u_ds, dl_bs, dl_ds, do_bs, do_ds, du_bs, du_ds, dd_bs, dd_ds;
+    int64_t B_bs, B_gs, B_ns, C_bs, C_gs, C_ns;
+    int softplus;
+    bool vec_ok;
+};
+
+int scan_fwd_launch(const ScanFwdParams& p, int dtype, cudaStream_t stream);
+int scan_bwd_launch(const ScanBwdParams& p, int dtype, cudaStream_t stream);
+
+}  // namespace vmb

@@ -1,0 +1,106 @@
+"""Thin torch-tensor front-end of the C-ABI (device pointers + strides -> library call).
+
+Mirrors the reference binding `selective_scan_cuda_core.fwd/bwd`
+(Mamba/kernels/selective_scan/csrc/selective_scan/cus/selective_scan.cpp:157-349): same argument
+meaning, same checks, same RuntimeError behaviour.  Outputs are allocated here with torch (the
+library owns nothing), on the input's device and current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.DT_F32, torch.bfloat16: _lib.DT_BF16, torch.float16: _lib.DT_F16}
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _check_common(u, delta, A, B, C_, D, delta_bias, who):
+    if u.dtype not in _DT:
+        raise RuntimeError(f"{who}: input dtype must be float32/float16/bfloat16, got {u.dtype}")
+    if A.dtype != torch.float32:
+        raise RuntimeError(f"{who}: A must be float32")
+    for n, t in (("delta", delta), ("B", B), ("C", C_)):
+        if t.dtype != u.dtype:
+            raise RuntimeError(f"{who}: {n}.dtype {t.dtype} != u.dtype {u.dtype}")
+    for n, t in (("u", u), ("delta", delta), ("A", A), ("B", B), ("C", C_)):
+        if not t.is_cuda:
+            raise RuntimeError(f"{who}: {n} must be a CUDA tensor")
+    if u.dim() != 3 or B.dim() != 4 or C_.dim() != 4 or A.dim() != 2:
+        raise RuntimeError(f"{who}: expected u (B,D,L), A (D,N), B/C (B,G,N,L)")
+    b, d, l = u.shape
+    n = A.shape[1]
+    g = B.shape[1]
+    if tuple(delta.shape) != (b, d, l) or tuple(A.shape) != (d, n) or tuple(B.shape) != (b, g, n, l) \
+            or tuple(C_.shape) != (b, g, n, l):
+        raise RuntimeError(f"{who}: shape mismatch u{tuple(u.shape)} delta{tuple(delta.shape)} A{tuple(A.shape)} "
+                           f"B{tuple(B.shape)} C{tuple(C_.shape)}")
+    for nme, t in (("u", u), ("delta", delta), ("B", B), ("C", C_)):
+        if t.stride(-1) != 1 and t.size(-1) != 1:
+            raise RuntimeError(f"{who}: {nme}.stride(-1) must be 1")
+    if not A.is_contiguous():
+        raise RuntimeError(f"{who}: A must be contiguous")
+    for nme, t in (("D", D), ("delta_bias", delta_bias)):
+        if t is not None:
+            if t.dtype != torch.float32 or not t.is_cuda or tuple(t.shape) != (d,) or not t.is_contiguous():
+                raise RuntimeError(f"{who}: {nme} must be a contiguous float32 CUDA tensor of shape ({d},)")
+    return b, d, l, n, g
+
+
+def ckpt_interval() -> int:
+    return _lib.lib().vmb_scan_ckpt_interval()
+
+
+def selective_scan_fwd(u, delta, A, B, C_, D=None, delta_bias=None, delta_softplus=False, need_ckpt=True):
+    """-> (out, ckpt).  out has delta's dtype/shape; ckpt is the opaque fp32 checkpoint tensor."""
+    b, d, l, n, g = _check_common(u, delta, A, B, C_, D, delta_bias, "selective_scan_fwd")
+    L = _lib.lib()
+    out = torch.empty_like(delta)
+    if out.stride(-1) != 1:
+        out = torch.empty(delta.shape, dtype=delta.dtype, device=delta.device)
+    ck = ckpt_interval()
+    ckpt = torch.empty((b, d, (l + ck - 1) // ck, n), dtype=torch.float32, device=u.device) if need_ckpt else None
+    a = _lib.ScanFwdArgs(
+        _ptr(u), _ptr(delta), _ptr(A), _ptr(B), _ptr(C_), _ptr(D), _ptr(delta_bias), _ptr(out), _ptr(ckpt),
+        b, d, l, n, g,
+        u.stride(0), u.stride(1), delta.stride(0), delta.stride(1), out.stride(0), out.stride(1),
+        B.stride(0), B.stride(1), B.stride(2), C_.stride(0), C_.stride(1), C_.stride(2),
+        int(bool(delta_softplus)), _DT[u.dtype])
+    with torch.cuda.device(u.device):
+        _lib.check(L.vmb_selective_scan_fwd(C.byref(a), _stream(u)), "selective_scan_fwd")
+    return out, ckpt
+
+
+def selective_scan_bwd(u, delta, A, B, C_, D, delta_bias, dout, ckpt, delta_softplus=False):
+    """-> (du, ddelta, dA, dB, dC, dD, ddelta_bias); dB/dC returned in B/C dtype (reference cpp:347)."""
+    b, d, l, n, g = _check_common(u, delta, A, B, C_, D, delta_bias, "selective_scan_bwd")
+    if dout.dtype != u.dtype or tuple(dout.shape) != (b, d, l) or (dout.stride(-1) != 1 and dout.size(-1) != 1):
+        raise RuntimeError("selective_scan_bwd: dout must match u in dtype/shape with stride(-1)==1")
+    L = _lib.lib()
+    du = torch.empty((b, d, l), dtype=u.dtype, device=u.device)
+    ddelta = torch.empty((b, d, l), dtype=u.dtype, device=u.device)
+    dA = torch.zeros_like(A)
+    dB = torch.zeros((b, g, n, l), dtype=torch.float32, device=u.device)
+    dC = torch.zeros((b, g, n, l), dtype=torch.float32, device=u.device)
+    dD = torch.zeros_like(D) if D is not None else None
+    dbias = torch.zeros_like(delta_bias) if delta_bias is not None else None
+    a = _lib.ScanBwdArgs(
+        _ptr(u), _ptr(delta), _ptr(A), _ptr(B), _ptr(C_), _ptr(D), _ptr(delta_bias), _ptr(dout), _ptr(ckpt),
+        _ptr(du), _ptr(ddelta), _ptr(dA), _ptr(dB), _ptr(dC), _ptr(dD), _ptr(dbias),
+        b, d, l, n, g,
+        u.stride(0), u.stride(1), delta.stride(0), delta.stride(1), dout.stride(0), dout.stride(1),
+        du.stride(0), du.stride(1), ddelta.stride(0), ddelta.stride(1),
+        B.stride(0), B.stride(1), B.stride(2), C_.stride(0), C_.stride(1), C_.stride(2),
+        int(bool(delta_softplus)), _DT[u.dtype])
+    with torch.cuda.device(u.device):
+        _lib.check(L.vmb_selective_scan_bwd(C.byref(a), _stream(u)), "selective_scan_bwd")
+    return du, ddelta, dA, dB.to(B.dtype), dC.to(C_.dtype), dD, dbias
