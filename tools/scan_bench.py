@@ -16,6 +16,7 @@ def bench(fn, iters=20, warmup=5, flush=None):
         if flush is not None:
             flush.zero_()
         s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+        torch.cuda._sleep(400_000)  # let the host run ahead so launch latency is not timed
         s.record(); fn(); e.record(); torch.cuda.synchronize()
         ts.append(s.elapsed_time(e))
     ts.sort()

@@ -133,6 +133,17 @@ __device__ __forceinline__ void load_vec(const T* __restrict__ p, float* f, int 
         for (int i = 0; i < V; ++i) f[i] = i < valid ? to_f32<T>(p[i]) : 0.f;
     }
 }
+// same, from shared memory (always 16 B aligned, always full)
+template <typename T>
+__device__ __forceinline__ void load_vec_smem(const T* p, float* f) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    if constexpr (sizeof(T) == 4) {
+        f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
+        f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+    } else {
+        unpack8<T>(v, f);
+    }
+}
 template <typename T>
 __device__ __forceinline__ void store_vec(T* __restrict__ p, const float* f, int valid, bool aligned) {
     constexpr int V = Vec<T>::N;

@@ -2,18 +2,21 @@
 // (reference: Mamba/kernels/selective_scan/csrc/selective_scan/cus/selective_scan_fwd_kernel.cuh:61-172).
 //
 // Design (B200-first, not a port of the CUB block-scan kernel):
-//   * one CTA = RB rows (channels d of one (batch, group)) x SEGS sequence segments of T=16
-//     positions; lane -> (row = lane % RB, segment = warp*(32/RB) + lane/RB).
+//   * one WARP (= one CTA of 32 threads) owns RB rows (channels d of one (batch, group)) and walks
+//     the sequence in warp-chunks of (32/RB) segments x T=16 positions;
+//     lane -> (row = lane % RB, segment = lane / RB).  No block-level barrier anywhere.
 //   * B/C for the group are staged once per chunk in shared memory as fp32 and read by
 //     BROADCAST (all rows of a warp read the same (n,l) word), so smem bandwidth is 1/RB of a
 //     row-per-warp design and L2 traffic for B/C is 1/RB of the reference's row-per-CTA design.
 //   * u/delta/out go straight between HBM and registers in full 32 B sectors (16 bf16 per lane).
 //   * two passes per state pair, both states packed in one fma.rn.f32x2:
 //       pass 1: a = ex2(A*log2e*dt) (MUFU), local end state with zero start;
-//       segment scan: shuffles inside the warp, a short sequential fold over warp totals in smem;
+//       segment scan: shuffles inside the warp; the chunk-to-chunk carry lives in the warp's smem;
 //       pass 2: h = a*h + b from the true start state, y += h*C.
 //     The decay of a whole segment is ex2(A * sum(dt)) -- one MUFU, no product chain.
 //   * checkpoints of h every CKPT positions (fp32) feed the backward kernel.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "scan_params.h"
 
@@ -21,26 +24,27 @@ namespace vmb {
 
 constexpr int T = kScanT;  // positions per lane per chunk
 
-template <int RB, int W>
+// One WARP is an autonomous unit: RB rows (channels of one (batch, group)) x SEGW = 32/RB
+// consecutive segments of T positions -> a warp-chunk of SEGW*T positions.  No block barriers:
+// warps de-synchronise, so MUFU-heavy pass 1 of one warp overlaps FMA-heavy pass 2 of another.
+template <int RB>
 struct FwdCfg {
     static constexpr int SEGW = 32 / RB;
-    static constexpr int SEGS = W * SEGW;
-    static constexpr int CHUNK = SEGS * T;
+    static constexpr int CHUNK = SEGW * T;
     static constexpr int SEGQ = T / 2 + 1;  // float4 slots per segment (one pad slot: conflict-free broadcast)
-    static constexpr int SLOTS = SEGS * SEGQ;
-    static size_t smem_bytes(int npad) {
-        return sizeof(float4) * (2 * 8 * SLOTS + 2 * W * RB) + sizeof(float) * (3 * RB * npad);
-    }
+    static constexpr int SLOTS = SEGW * SEGQ;
+    static size_t smem_bytes(int npad) { return sizeof(float4) * (2 * 8 * SLOTS) + sizeof(float) * (2 * RB * npad); }
 };
 
-// Stage B or C rows [n0, n0+16) x [c0, c0+CHUNK) of one (batch, group) into smem as
+// Stage B or C rows [n0, n0+16) x [c0, c0+CHUNK) of one (batch, group) into the warp's smem as
 // float4 = (X[n][l], X[n+1][l], X[n][l+1], X[n+1][l+1]) at [n/2][seg*SEGQ + (l%T)/2].
-template <typename in_t, typename Cfg, int NTHREADS>
-__device__ __forceinline__ void stage_bc(float4* __restrict__ dst, const in_t* __restrict__ src,
-                                         int64_t n_stride, int n0, int N, int c0, int L, bool vec_ok) {
+template <typename in_t, typename Cfg>
+__device__ __forceinline__ void stage_bc(float4* __restrict__ dst, const in_t* __restrict__ src, int64_t n_stride,
+                                         int n0, int N, int c0, int L, bool vec_ok, int lane) {
     constexpr int V = Vec<in_t>::N;
     constexpr int LG = Cfg::CHUNK / V;  // l-groups per row
-    for (int it = threadIdx.x; it < 8 * LG; it += NTHREADS) {
+#pragma unroll
+    for (int it = lane; it < 8 * LG; it += 32) {
         const int np = it / LG, lg = it % LG;
         const int l = lg * V;  // offset inside chunk
         const int n = n0 + 2 * np;
@@ -63,35 +67,99 @@ __device__ __forceinline__ void stage_bc(float4* __restrict__ dst, const in_t* _
     }
 }
 
-template <typename in_t, int RB, int W>
-__global__ void __launch_bounds__(W * 32, (W <= 8 ? 2 : 1))
-scan_fwd_kernel(const ScanFwdParams p) {
-    using Cfg = FwdCfg<RB, W>;
+// cp.async (LDGSTS) 16-byte copy, zero-filling bytes beyond src_bytes.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Raw (input dtype) staging buffer of one warp-chunk, filled asynchronously one chunk ahead:
+// rows [0,RB) = u, [RB,2RB) = delta, [2RB,2RB+16) = B states 0..15, [2RB+16,2RB+32) = C states 0..15.
+template <typename in_t, int RB>
+struct RawCfg {
+    static constexpr int V = Vec<in_t>::N;
+    static constexpr int CHUNK = FwdCfg<RB>::CHUNK;
+    static constexpr int PITCH = CHUNK + V;  // +16 B: conflict-free row-strided 128-bit reads
+    static constexpr int ROWS = 2 * RB + 32;
+    static constexpr size_t bytes = sizeof(in_t) * (size_t)ROWS * PITCH;
+};
+
+template <typename in_t, int RB>
+__device__ __forceinline__ void prefetch_chunk(in_t* __restrict__ raw, const in_t* __restrict__ ubase,
+                                               const in_t* __restrict__ dbase, int64_t u_ds, int64_t dl_ds,
+                                               const in_t* __restrict__ Bg, const in_t* __restrict__ Cg, int64_t B_ns,
+                                               int64_t C_ns, int N, int c0, int L, int lane) {
+    using R = RawCfg<in_t, RB>;
+    constexpr int V = R::V, OPR = R::CHUNK / V;  // 16-byte ops per row
+#pragma unroll
+    for (int it = lane; it < R::ROWS * OPR; it += 32) {
+        const int row = it / OPR, l = (it % OPR) * V;
+        const in_t* src;
+        bool row_ok = true;
+        if (row < RB) src = ubase + (int64_t)row * u_ds;
+        else if (row < 2 * RB) src = dbase + (int64_t)(row - RB) * dl_ds;
+        else if (row < 2 * RB + 16) { src = Bg + (int64_t)(row - 2 * RB) * B_ns; row_ok = (row - 2 * RB) < N; }
+        else { src = Cg + (int64_t)(row - 2 * RB - 16) * C_ns; row_ok = (row - 2 * RB - 16) < N; }
+        int nbytes = (L - (c0 + l)) * (int)sizeof(in_t);
+        nbytes = row_ok ? min(max(nbytes, 0), 16) : 0;
+        cp_async16(raw + row * R::PITCH + l, nbytes > 0 ? (const void*)(src + c0 + l) : (const void*)ubase, nbytes);
+    }
+    cp_async_commit();
+}
+
+// raw B/C rows (states 0..15 of this chunk) -> fp32 float4 layout used by the passes
+template <typename in_t, int RB>
+__device__ __forceinline__ void convert_bc(float4* __restrict__ dst, const in_t* __restrict__ rawX, int lane) {
+    using R = RawCfg<in_t, RB>;
+    using Cfg = FwdCfg<RB>;
+    constexpr int V = R::V, LG = R::CHUNK / V;
+#pragma unroll
+    for (int it = lane; it < 8 * LG; it += 32) {
+        const int np = it / LG, l = (it % LG) * V;
+        float f0[V], f1[V];
+        load_vec_smem<in_t>(rawX + (2 * np) * R::PITCH + l, f0);
+        load_vec_smem<in_t>(rawX + (2 * np + 1) * R::PITCH + l, f1);
+        float4* d = dst + np * Cfg::SLOTS + (l / T) * Cfg::SEGQ + (l % T) / 2;
+#pragma unroll
+        for (int i = 0; i < V / 2; ++i) d[i] = make_float4(f0[2 * i], f1[2 * i], f0[2 * i + 1], f1[2 * i + 1]);
+    }
+}
+
+template <typename in_t, int RB>
+__global__ void __launch_bounds__(32, 16) scan_fwd_kernel(const ScanFwdParams p) {
+    using Cfg = FwdCfg<RB>;
+    using R = RawCfg<in_t, RB>;
     constexpr int SEGW = Cfg::SEGW, CHUNK = Cfg::CHUNK, SEGQ = Cfg::SEGQ, SLOTS = Cfg::SLOTS;
-    constexpr int NTHREADS = W * 32;
     constexpr int V = Vec<in_t>::N;
 
     extern __shared__ float4 smem_f4[];
-    float4* sB = smem_f4;
-    float4* sC = sB + 8 * SLOTS;
-    float4* sAgg = sC + 8 * SLOTS;                                // [2][W][RB]
-    float* sCarry = reinterpret_cast<float*>(sAgg + 2 * W * RB);  // [2][RB][npad]
-    float* sA = sCarry + 2 * RB * p.npad;                         // [RB][npad]
+    float4* sB = smem_f4;                                         // [8][SLOTS]
+    float4* sC = sB + 8 * SLOTS;                                  // [8][SLOTS]
+    in_t* raw = reinterpret_cast<in_t*>(sC + 8 * SLOTS);          // RawCfg rows
+    float* sCarry = reinterpret_cast<float*>(reinterpret_cast<char*>(raw) + R::bytes);  // [RB][npad]
+    float* sA = sCarry + RB * p.npad;                             // [RB][npad]  A * log2(e)
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int r = lane % RB, sl = lane / RB, seg = warp * SEGW + sl;
-    const int b = blockIdx.y;
-    const int d0 = blockIdx.x * RB, d = d0 + r;
+    const int lane = threadIdx.x;
+    const int r = lane % RB, sl = lane / RB;
+    const int blocks_per_batch = p.dim / RB;
+    const int b = blockIdx.x / blocks_per_batch;
+    const int d0 = (blockIdx.x % blocks_per_batch) * RB, d = d0 + r;
     const int g = d0 / p.rows_per_group;
     const int N = p.N, L = p.L, npad = p.npad;
+    const bool async_ok = p.vec_ok;  // 16 B-aligned rows: asynchronous prefetch path
 
     const in_t* __restrict__ Bg = reinterpret_cast<const in_t*>(p.Bm) + (int64_t)b * p.B_bs + (int64_t)g * p.B_gs;
     const in_t* __restrict__ Cg = reinterpret_cast<const in_t*>(p.Cm) + (int64_t)b * p.C_bs + (int64_t)g * p.C_gs;
-    const in_t* __restrict__ urow = reinterpret_cast<const in_t*>(p.u) + (int64_t)b * p.u_bs + (int64_t)d * p.u_ds;
-    const in_t* __restrict__ drow = reinterpret_cast<const in_t*>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)d * p.dl_ds;
+    const in_t* __restrict__ ublk = reinterpret_cast<const in_t*>(p.u) + (int64_t)b * p.u_bs + (int64_t)d0 * p.u_ds;
+    const in_t* __restrict__ dblk = reinterpret_cast<const in_t*>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)d0 * p.dl_ds;
+    const in_t* __restrict__ urow = ublk + (int64_t)r * p.u_ds;
+    const in_t* __restrict__ drow = dblk + (int64_t)r * p.dl_ds;
     in_t* __restrict__ orow = reinterpret_cast<in_t*>(p.out) + (int64_t)b * p.o_bs + (int64_t)d * p.o_ds;
 
-    for (int i = tid; i < RB * npad; i += NTHREADS) {
+    if (async_ok) prefetch_chunk<in_t, RB>(raw, ublk, dblk, p.u_ds, p.dl_ds, Bg, Cg, p.B_ns, p.C_ns, N, 0, L, lane);
+    for (int i = lane; i < RB * npad; i += 32) {
         const int rr = i / npad, n = i % npad;
         sA[i] = n < N ? p.A[(int64_t)(d0 + rr) * N + n] * kLog2e : 0.f;
         sCarry[i] = 0.f;
@@ -100,19 +168,33 @@ scan_fwd_kernel(const ScanFwdParams p) {
     const float bias = p.bias ? p.bias[d] : 0.f;
     const int ntiles = npad / 16;
 
-    int pc = 0;
-    for (int c0 = 0; c0 < L; c0 += CHUNK, pc ^= 1) {
-        const int l0 = c0 + seg * T;
+    for (int c0 = 0; c0 < L; c0 += CHUNK) {
+        const int l0 = c0 + sl * T;
         const int valid = min(max(L - l0, 0), T);
         float uv[T], dt[T];
+        if (async_ok) {
+            cp_async_wait_all();
+            __syncwarp();
+            convert_bc<in_t, RB>(sB, raw + (2 * RB) * R::PITCH, lane);
+            convert_bc<in_t, RB>(sC, raw + (2 * RB + 16) * R::PITCH, lane);
 #pragma unroll
-        for (int v = 0; v < T / V; ++v) {
-            load_vec<in_t>(urow + l0 + v * V, uv + v * V, valid - v * V, p.vec_ok);
-            load_vec<in_t>(drow + l0 + v * V, dt + v * V, valid - v * V, p.vec_ok);
+            for (int v = 0; v < T / V; ++v) {
+                load_vec_smem<in_t>(raw + r * R::PITCH + sl * T + v * V, uv + v * V);
+                load_vec_smem<in_t>(raw + (RB + r) * R::PITCH + sl * T + v * V, dt + v * V);
+            }
+            __syncwarp();  // raw buffer fully consumed -> refill it with the next chunk while we compute
+            if (c0 + CHUNK < L)
+                prefetch_chunk<in_t, RB>(raw, ublk, dblk, p.u_ds, p.dl_ds, Bg, Cg, p.B_ns, p.C_ns, N, c0 + CHUNK, L, lane);
+        } else {
+#pragma unroll
+            for (int v = 0; v < T / V; ++v) {
+                load_vec<in_t>(urow + l0 + v * V, uv + v * V, valid - v * V, false);
+                load_vec<in_t>(drow + l0 + v * V, dt + v * V, valid - v * V, false);
+            }
         }
         float sigma = 0.f;
         float dtu[T];
-        float2 y2[T];
+        float y[T];  // scalar accumulators (a packed pair per position would cost 16 more registers)
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             float x = dt[t] + bias;
@@ -121,21 +203,23 @@ scan_fwd_kernel(const ScanFwdParams p) {
             dt[t] = x;
             dtu[t] = x * uv[t];
             sigma += x;
-            y2[t] = make_float2(0.f, 0.f);
+            y[t] = Dval * uv[t];
         }
 
         for (int nt = 0; nt < ntiles; ++nt) {
-            __syncthreads();  // previous tile (and sAgg / carry buffers) fully consumed
-            stage_bc<in_t, Cfg, NTHREADS>(sB, Bg, p.B_ns, nt * 16, N, c0, L, p.vec_ok);
-            stage_bc<in_t, Cfg, NTHREADS>(sC, Cg, p.C_ns, nt * 16, N, c0, L, p.vec_ok);
-            __syncthreads();
+            if (!async_ok || nt > 0) {  // synchronous staging: unaligned tensors, or state tiles beyond the first
+                __syncwarp();
+                stage_bc<in_t, Cfg>(sB, Bg, p.B_ns, nt * 16, N, c0, L, p.vec_ok, lane);
+                stage_bc<in_t, Cfg>(sC, Cg, p.C_ns, nt * 16, N, c0, L, p.vec_ok, lane);
+            }
+            __syncwarp();
 
 #pragma unroll 1
             for (int np = 0; np < 8; ++np) {
                 const int n0 = nt * 16 + 2 * np;
                 const float2 A2 = *reinterpret_cast<const float2*>(&sA[r * npad + n0]);
-                const float4* __restrict__ bq = sB + np * SLOTS + seg * SEGQ;
-                const float4* __restrict__ cq = sC + np * SLOTS + seg * SEGQ;
+                const float4* __restrict__ bq = sB + np * SLOTS + sl * SEGQ;
+                const float4* __restrict__ cq = sC + np * SLOTS + sl * SEGQ;
                 // ---- pass 1: decay factors + local end state ----
                 float2 a2[T];
                 float2 hend = make_float2(0.f, 0.f);
@@ -160,32 +244,26 @@ scan_fwd_kernel(const ScanFwdParams p) {
                         P2 = mul2(P2, Pp);
                     }
                 }
-                const int buf = np & 1;
-                if (sl == SEGW - 1) sAgg[(buf * W + warp) * RB + r] = make_float4(P2.x, P2.y, hend.x, hend.y);
                 float2 Pe = shfl_up2(P2, RB % 32), He = shfl_up2(hend, RB % 32);
                 if (lane < RB) {
                     Pe = make_float2(1.f, 1.f);
                     He = make_float2(0.f, 0.f);
                 }
-                __syncthreads();
-                // ---- fold the totals of the preceding warps onto the chunk-start state ----
-                float2 st = *reinterpret_cast<const float2*>(&sCarry[(pc * RB + r) * npad + n0]);
-                for (int w2 = 0; w2 < warp; ++w2) {
-                    const float4 q = sAgg[(buf * W + w2) * RB + r];
-                    st = fma2(make_float2(q.x, q.y), st, make_float2(q.z, q.w));
-                }
+                // ---- chunk-start state (written by the last segment's lanes one chunk ago) ----
+                float2* carry = reinterpret_cast<float2*>(&sCarry[r * npad + n0]);
+                const float2 st = *carry;
                 float2 h = fma2(Pe, st, He);
-                if (warp == W - 1 && sl == SEGW - 1)
-                    *reinterpret_cast<float2*>(&sCarry[((pc ^ 1) * RB + r) * npad + n0]) = fma2(P2, st, hend);
+                __syncwarp();
+                if (sl == SEGW - 1) *carry = fma2(P2, st, hend);
                 // ---- pass 2: true states, output contraction ----
 #pragma unroll
                 for (int t = 0; t < T; t += 2) {
                     const float4 Bq = bq[t / 2];
                     const float4 Cq = cq[t / 2];
                     h = fma2(a2[t], h, mul2(make_float2(dtu[t], dtu[t]), make_float2(Bq.x, Bq.y)));
-                    y2[t] = fma2(h, make_float2(Cq.x, Cq.y), y2[t]);
+                    y[t] = fmaf(h.y, Cq.y, fmaf(h.x, Cq.x, y[t]));
                     h = fma2(a2[t + 1], h, mul2(make_float2(dtu[t + 1], dtu[t + 1]), make_float2(Bq.z, Bq.w)));
-                    y2[t + 1] = fma2(h, make_float2(Cq.z, Cq.w), y2[t + 1]);
+                    y[t + 1] = fmaf(h.y, Cq.w, fmaf(h.x, Cq.z, y[t + 1]));
                 }
                 if (p.ckpt != nullptr && l0 < L && ((l0 + T) % kScanCkpt) == 0) {
                     float* ck = p.ckpt + (((int64_t)b * p.dim + d) * p.n_ckpt + ((l0 + T) / kScanCkpt - 1)) * N + n0;
@@ -194,64 +272,59 @@ scan_fwd_kernel(const ScanFwdParams p) {
                 }
             }
         }
-        float yo[T];
 #pragma unroll
-        for (int t = 0; t < T; ++t) yo[t] = fmaf(Dval, uv[t], y2[t].x + y2[t].y);
-#pragma unroll
-        for (int v = 0; v < T / V; ++v) store_vec<in_t>(orow + l0 + v * V, yo + v * V, valid - v * V, p.vec_ok);
+        for (int v = 0; v < T / V; ++v) store_vec<in_t>(orow + l0 + v * V, y + v * V, valid - v * V, p.vec_ok);
     }
 }
 
-template <typename in_t, int RB, int W>
+template <typename in_t, int RB>
 static int launch_cfg(const ScanFwdParams& p, cudaStream_t stream) {
-    using Cfg = FwdCfg<RB, W>;
-    auto kern = scan_fwd_kernel<in_t, RB, W>;
-    const size_t smem = Cfg::smem_bytes(p.npad);
+    using Cfg = FwdCfg<RB>;
+    auto kern = scan_fwd_kernel<in_t, RB>;
+    const size_t smem = Cfg::smem_bytes(p.npad) + RawCfg<in_t, RB>::bytes;
     VMB_CHECK(smem <= 227 * 1024, "selective_scan_fwd: dstate=%d needs %zu B of shared memory", p.N, smem);
-    VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(p.dim / RB, p.batch);
-    kern<<<grid, W * 32, smem, stream>>>(p);
+    if (smem > 48 * 1024) VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long blocks = (long)p.batch * (p.dim / RB);
+    kern<<<(unsigned)blocks, 32, smem, stream>>>(p);
     VMB_CUDA(cudaGetLastError());
     return VMB_OK;
 }
 
-// Pick rows-per-CTA: must divide the rows of a group; prefer long chunks (fewer barriers per
-// position) unless the sequence is short or the grid would leave SMs idle.
+// Rows per warp: must divide the rows of a group.  Larger RB = less smem/L2 traffic for B/C and
+// fewer shuffle steps; smaller RB = more warps (parallelism) and longer warp-chunks.  Aim for
+// >= ~12 warps per SM, fall back to the smallest admissible RB for small problems.
 static int pick_rb(const ScanFwdParams& p) {
     const int rpg = p.rows_per_group;
-    int best = 0;
-    double best_score = -1.0;
-    const int cands[6] = {8, 16, 32, 4, 2, 1};
-    for (int i = 0; i < 6; ++i) {
-        const int rb = cands[i];
-        if (rpg % rb) continue;
-        const int w = rb >= 8 ? 8 : rb;  // threads = 32*w
-        const int chunk = (32 / rb) * w * T;
-        const long ctas = (long)p.batch * (p.dim / rb);
-        const long slots = 148L * (rb >= 8 ? 2 : 4);
-        const double eff = (double)ctas / (double)(((ctas + slots - 1) / slots) * slots);
-        // wasted lanes when the chunk overshoots a short sequence
-        const int nchunks = (p.L + chunk - 1) / chunk;
-        const double fill = (double)p.L / ((double)nchunks * chunk);
-        double score = eff * fill * (rb >= 8 ? 1.0 : 0.5) * (rb == 8 ? 1.05 : 1.0);
-        if (score > best_score) { best_score = score; best = rb; }
+    if (const char* e = getenv("VMB_SCAN_RB")) {  // tuning/debug override
+        const int rb = atoi(e);
+        if (rb > 0 && rb <= 32 && (rb & (rb - 1)) == 0 && rpg % rb == 0) return rb;
     }
-    return best;
+    const long rows = (long)p.batch * p.dim;
+    // measured on B200 (C=96, L=4096): RB=8 wins once there are >= ~6 warps per SM, RB=4 below that;
+    // RB<4 only when the group has fewer rows (their warp-chunks need > 50 KB of smem per warp).
+    int rb = 1;
+    while (rb < 8 && rpg % (rb * 2) == 0) rb *= 2;
+    if (rb == 8 && rows / 8 < 148L * 6 && rpg % 4 == 0) rb = 4;
+    if (rb == 8 && rpg % 16 == 0 && rows / 16 >= 148L * 64) rb = 16;
+    // short sequences: do not use a warp-chunk much longer than L
+    while (rb < 32 && rpg % (rb * 2) == 0 && (32 / rb) * T >= 2 * p.L) rb *= 2;
+    return rb;
 }
 
 template <typename in_t>
 static int launch_t(const ScanFwdParams& p, cudaStream_t stream) {
     switch (pick_rb(p)) {
-        case 32: return launch_cfg<in_t, 32, 8>(p, stream);
-        case 16: return launch_cfg<in_t, 16, 8>(p, stream);
-        case 8: return launch_cfg<in_t, 8, 8>(p, stream);
-        case 4: return launch_cfg<in_t, 4, 4>(p, stream);
-        case 2: return launch_cfg<in_t, 2, 2>(p, stream);
-        default: return launch_cfg<in_t, 1, 1>(p, stream);
+        case 32: return launch_cfg<in_t, 32>(p, stream);
+        case 16: return launch_cfg<in_t, 16>(p, stream);
+        case 8: return launch_cfg<in_t, 8>(p, stream);
+        case 4: return launch_cfg<in_t, 4>(p, stream);
+        case 2: return launch_cfg<in_t, 2>(p, stream);
+        default: return launch_cfg<in_t, 1>(p, stream);
     }
 }
 
 int scan_fwd_launch(const ScanFwdParams& p, int dtype, cudaStream_t stream) {
+    VMB_CHECK((long)p.batch * p.dim < (1L << 31), "selective_scan_fwd: batch*dim too large");
     switch (dtype) {
         case VMB_F32: return launch_t<float>(p, stream);
         case VMB_BF16: return launch_t<__nv_bfloat16>(p, stream);
