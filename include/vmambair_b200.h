@@ -64,13 +64,16 @@ int vmb_selective_scan_fwd(const vmb_scan_fwd_args* a, void* stream);
  *   dout, du, ddelta : (batch, dim, seqlen) dtype `dt`
  *   dA (dim,dstate), dD (dim), ddelta_bias (dim): fp32, ACCUMULATED into (caller zero-fills,
  *       like the reference's torch::zeros_like, cpp:321-327)
- *   dB, dC : fp32 (batch, ngroups, dstate, seqlen) contiguous, ACCUMULATED into (caller zero-fills
- *       and casts afterwards, cpp:322-323,347)
+ *   dB, dC : (batch, ngroups, dstate, seqlen) contiguous, dtype `dt`, fully written (the reference
+ *       accumulates in fp32 and casts in torch, cpp:322-323,347; here the fp32 accumulation lives in
+ *       `workspace` and the cast is done by the library)
+ *   workspace : device scratch of vmb_scan_bwd_workspace_bytes(...) bytes, 16 B aligned; the library
+ *       zero-fills it on `stream`
  *   ckpt  : as written by the forward (required when seqlen > interval). */
 typedef struct {
     const void* u; const void* delta; const float* A; const void* Bm; const void* Cm;
     const float* D; const float* delta_bias; const void* dout; const float* ckpt;
-    void* du; void* ddelta; float* dA; float* dB; float* dC; float* dD; float* ddelta_bias;
+    void* du; void* ddelta; float* dA; void* dB; void* dC; float* dD; float* ddelta_bias; void* workspace;
     int batch, dim, seqlen, dstate, ngroups;
     int64_t u_bs, u_ds, delta_bs, delta_ds, dout_bs, dout_ds;
     int64_t du_bs, du_ds, ddelta_bs, ddelta_ds;
@@ -79,6 +82,7 @@ typedef struct {
     int dtype;
 } vmb_scan_bwd_args;
 int vmb_selective_scan_bwd(const vmb_scan_bwd_args* a, void* stream);
+int64_t vmb_scan_bwd_workspace_bytes(int batch, int ngroups, int dstate, int seqlen);
 
 #ifdef __cplusplus
 }

@@ -148,3 +148,83 @@ def test_errors_raise():
         ops.selective_scan_fwd(u, delta, A, Bm[:, :, :8], Cm, Dv, bias, True)
     with pytest.raises(RuntimeError):
         ops.selective_scan_fwd(u.double(), delta.double(), A, Bm.double(), Cm.double(), Dv, bias, True)
+
+
+# ----------------------------------------------------------------------------- backward
+BWD_TOL = {torch.float32: 2e-3, torch.float16: 6e-3, torch.bfloat16: 4e-2}
+
+
+def run_ours_bwd(u, delta, A, Bm, Cm, Dv, bias, dout, softplus):
+    from vmambair_b200 import ops
+    mv = lambda t: None if t is None else t.cuda()
+    a = [mv(t) for t in (u, delta, A, Bm, Cm, Dv, bias)]
+    out, ckpt = ops.selective_scan_fwd(*a, softplus, True)
+    grads = ops.selective_scan_bwd(*a, mv(dout), ckpt, softplus)
+    torch.cuda.synchronize()
+    return out, grads
+
+
+def check_grads(got, ref, dtype, names=("du", "ddelta", "dA", "dB", "dC", "dD", "dbias")):
+    tol = BWD_TOL[dtype]
+    for n, g, r in zip(names, got, ref):
+        if r is None:
+            assert g is None, n
+            continue
+        g = g.double().cpu()
+        r = r.double()
+        scale = r.abs().max().clamp_min(1e-6)
+        err = (g - r).abs().max()
+        # scale-aware bound (reference test uses rtol up to 5x / atol up to 10x of its output tolerance, :490-502)
+        assert err <= tol * scale + 1e-5, f"{n}: max err {err:.3e} vs scale {scale:.3e} (tol {tol})"
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c", "d", "e"])
+def test_bwd_golden_vectors(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, "scan_cases.npz"))
+    g = lambda k: torch.from_numpy(z[f"{name}/{k}"]) if f"{name}/{k}" in z else None
+    sp = bool(z[f"{name}/softplus"])
+    _, grads = run_ours_bwd(g("u"), g("delta"), g("A"), g("B"), g("C"), g("D"), g("bias"), g("dout"), sp)
+    ref = [g(k) for k in ("du", "ddelta", "dA", "dB", "dC", "dD", "dbias")]
+    check_grads(grads, ref, torch.float32)
+
+
+BWD_SHAPES = [
+    (2, 32, 64, 16, 4),
+    (1, 64, 1000, 16, 2),
+    (1, 192, 2048, 16, 4),
+    (3, 8, 96, 16, 2),
+    (2, 2, 48, 16, 2),
+    (1, 24, 300, 1, 1),
+    (1, 16, 200, 40, 2),
+    (1, 6, 513, 16, 3),
+]
+
+
+@pytest.mark.parametrize("shape", BWD_SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("softplus", [True, False])
+def test_bwd_vs_oracle(shape, dtype, softplus):
+    b, D, L, N, G = shape
+    ins = make_inputs(b, D, L, N, G, dtype, seed=L + 1)
+    dout = torch.randn(b, D, L, generator=torch.Generator().manual_seed(L)).to(dtype)
+    _, grads = run_ours_bwd(*ins, dout, softplus)
+    ref = cscan.scan_bwd(*ins, dout, softplus)
+    check_grads(grads, ref, dtype)
+
+
+def test_bwd_optional_args_none():
+    ins = make_inputs(2, 16, 130, 16, 2, torch.float32, seed=4, has_D=False, has_bias=False)
+    dout = torch.randn(2, 16, 130)
+    _, grads = run_ours_bwd(*ins, dout, True)
+    ref = cscan.scan_bwd(*ins, dout, True)
+    assert grads[5] is None and grads[6] is None
+    check_grads(grads, ref, torch.float32)
+
+
+def test_bwd_model_like_full_row():
+    """C=48 OSS scan shape, model-like distribution, fp32."""
+    ins = make_inputs(1, 192, 4096, 16, 4, torch.float32, seed=11, model_like=True)
+    dout = torch.randn(1, 192, 4096, generator=torch.Generator().manual_seed(1))
+    _, grads = run_ours_bwd(*ins, dout, True)
+    ref = cscan.scan_bwd(*ins, dout, True)
+    check_grads(grads, ref, torch.float32)

@@ -32,7 +32,7 @@ class ScanBwdArgs(C.Structure):
     _fields_ = [
         ("u", vp), ("delta", vp), ("A", vp), ("Bm", vp), ("Cm", vp), ("D", vp), ("delta_bias", vp),
         ("dout", vp), ("ckpt", vp),
-        ("du", vp), ("ddelta", vp), ("dA", vp), ("dB", vp), ("dC", vp), ("dD", vp), ("ddelta_bias", vp),
+        ("du", vp), ("ddelta", vp), ("dA", vp), ("dB", vp), ("dC", vp), ("dD", vp), ("ddelta_bias", vp), ("workspace", vp),
         ("batch", C.c_int), ("dim", C.c_int), ("seqlen", C.c_int), ("dstate", C.c_int), ("ngroups", C.c_int),
         ("u_bs", i64), ("u_ds", i64), ("delta_bs", i64), ("delta_ds", i64), ("dout_bs", i64), ("dout_ds", i64),
         ("du_bs", i64), ("du_ds", i64), ("ddelta_bs", i64), ("ddelta_ds", i64),
@@ -48,6 +48,7 @@ SYMBOLS = {
     "vmb_scan_ckpt_interval": (C.c_int, []),
     "vmb_selective_scan_fwd": (C.c_int, [C.POINTER(ScanFwdArgs), vp]),
     "vmb_selective_scan_bwd": (C.c_int, [C.POINTER(ScanBwdArgs), vp]),
+    "vmb_scan_bwd_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
 }
 
 

@@ -52,11 +52,16 @@ extern "C" int vmb_selective_scan_fwd(const vmb_scan_fwd_args* a, void* stream) 
     return scan_fwd_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int64_t vmb_scan_bwd_workspace_bytes(int batch, int ngroups, int dstate, int seqlen) {
+    const int64_t npad = (dstate + 15) / 16 * 16;
+    return 16 * (int64_t)batch * ngroups * (npad / 2) * seqlen;
+}
+
 extern "C" int vmb_selective_scan_bwd(const vmb_scan_bwd_args* a, void* stream) {
     VMB_CHECK(a != nullptr, "selective_scan_bwd: null args");
     VMB_CHECK(a->dtype == VMB_F32 || a->dtype == VMB_BF16 || a->dtype == VMB_F16,
               "selective_scan_bwd: dtype must be f32/bf16/f16 (got %d)", a->dtype);
-    VMB_CHECK(a->u && a->delta && a->A && a->Bm && a->Cm && a->dout && a->du && a->ddelta && a->dA && a->dB && a->dC,
+    VMB_CHECK(a->u && a->delta && a->A && a->Bm && a->Cm && a->dout && a->du && a->ddelta && a->dA && a->dB && a->dC && a->workspace,
               "selective_scan_bwd: null tensor pointer");
     VMB_CHECK(a->batch > 0 && a->dim > 0 && a->seqlen > 0 && a->dstate > 0 && a->ngroups > 0,
               "selective_scan_bwd: non-positive size");
@@ -65,13 +70,14 @@ extern "C" int vmb_selective_scan_bwd(const vmb_scan_bwd_args* a, void* stream) 
     VMB_CHECK(a->batch <= 65535, "selective_scan_bwd: batch > 65535");
     VMB_CHECK(a->ckpt != nullptr || a->seqlen <= kScanCkpt,
               "selective_scan_bwd: forward checkpoints required when seqlen > %d", kScanCkpt);
+    VMB_CHECK(aligned16(a->workspace), "selective_scan_bwd: workspace must be 16-byte aligned");
     VMB_CHECK((a->D == nullptr) == (a->dD == nullptr), "selective_scan_bwd: D and dD must both be given or both be NULL");
     VMB_CHECK((a->delta_bias == nullptr) == (a->ddelta_bias == nullptr),
               "selective_scan_bwd: delta_bias and ddelta_bias must both be given or both be NULL");
     ScanBwdParams p{};
     p.u = a->u; p.delta = a->delta; p.Bm = a->Bm; p.Cm = a->Cm; p.dout = a->dout; p.A = a->A; p.D = a->D;
     p.bias = a->delta_bias; p.ckpt = a->ckpt; p.du = a->du; p.ddelta = a->ddelta; p.dA = a->dA; p.dB = a->dB; p.dC = a->dC;
-    p.dD = a->dD; p.dbias = a->ddelta_bias;
+    p.dD = a->dD; p.dbias = a->ddelta_bias; p.dBC = static_cast<float*>(a->workspace);
     p.batch = a->batch; p.dim = a->dim; p.L = a->seqlen; p.N = a->dstate; p.G = a->ngroups;
     p.npad = (a->dstate + 15) / 16 * 16;
     p.rows_per_group = a->dim / a->ngroups;
@@ -83,7 +89,7 @@ extern "C" int vmb_selective_scan_bwd(const vmb_scan_bwd_args* a, void* stream) 
     const int v = 16 / elt_size(a->dtype);
     auto mult = [v](int64_t s) { return s % v == 0; };
     p.vec_ok = aligned16(a->u) && aligned16(a->delta) && aligned16(a->Bm) && aligned16(a->Cm) && aligned16(a->dout) &&
-               aligned16(a->du) && aligned16(a->ddelta) && mult(a->u_bs) && mult(a->u_ds) && mult(a->delta_bs) &&
+               aligned16(a->du) && aligned16(a->ddelta) && aligned16(a->workspace) && mult(a->u_bs) && mult(a->u_ds) && mult(a->delta_bs) &&
                mult(a->delta_ds) && mult(a->dout_bs) && mult(a->dout_ds) && mult(a->du_bs) && mult(a->du_ds) &&
                mult(a->ddelta_bs) && mult(a->ddelta_ds) && mult(a->B_bs) && mult(a->B_gs) && mult(a->B_ns) &&
                mult(a->C_bs) && mult(a->C_gs) && mult(a->C_ns);

@@ -6,7 +6,7 @@
 namespace vmb {
 
 constexpr int kScanT = 16;      // sequence positions per lane per chunk
-constexpr int kScanCkpt = 256;  // checkpoint interval (positions); see vmb_scan_ckpt_interval()
+constexpr int kScanCkpt = 64;   // checkpoint interval (positions); see vmb_scan_ckpt_interval()
 
 struct ScanFwdParams {
     const void *u, *delta, *Bm, *Cm;
@@ -23,8 +23,9 @@ struct ScanFwdParams {
 struct ScanBwdParams {
     const void *u, *delta, *Bm, *Cm, *dout;
     const float *A, *D, *bias, *ckpt;
-    void *du, *ddelta;
-    float *dA, *dB, *dC, *dD, *dbias;
+    void *du, *ddelta, *dB, *dC;  // I/O dtype
+    float *dA, *dD, *dbias;      // fp32, accumulated into
+    float* dBC;                  // fp32 scratch [b][g][npad/2][L][4], zeroed by the launcher
     int batch, dim, L, N, G, npad, rows_per_group, n_ckpt;
     int64_t u_bs, u_ds, dl_bs, dl_ds, do_bs, do_ds, du_bs, du_ds, dd_bs, dd_ds;
     int64_t B_bs, B_gs, B_ns, C_bs, C_gs, C_ns;

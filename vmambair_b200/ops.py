@@ -89,13 +89,14 @@ def selective_scan_bwd(u, delta, A, B, C_, D, delta_bias, dout, ckpt, delta_soft
     du = torch.empty((b, d, l), dtype=u.dtype, device=u.device)
     ddelta = torch.empty((b, d, l), dtype=u.dtype, device=u.device)
     dA = torch.zeros_like(A)
-    dB = torch.zeros((b, g, n, l), dtype=torch.float32, device=u.device)
-    dC = torch.zeros((b, g, n, l), dtype=torch.float32, device=u.device)
+    dB = torch.empty((b, g, n, l), dtype=u.dtype, device=u.device)
+    dC = torch.empty((b, g, n, l), dtype=u.dtype, device=u.device)
+    ws = torch.empty(L.vmb_scan_bwd_workspace_bytes(b, g, n, l), dtype=torch.uint8, device=u.device)
     dD = torch.zeros_like(D) if D is not None else None
     dbias = torch.zeros_like(delta_bias) if delta_bias is not None else None
     a = _lib.ScanBwdArgs(
         _ptr(u), _ptr(delta), _ptr(A), _ptr(B), _ptr(C_), _ptr(D), _ptr(delta_bias), _ptr(dout), _ptr(ckpt),
-        _ptr(du), _ptr(ddelta), _ptr(dA), _ptr(dB), _ptr(dC), _ptr(dD), _ptr(dbias),
+        _ptr(du), _ptr(ddelta), _ptr(dA), _ptr(dB), _ptr(dC), _ptr(dD), _ptr(dbias), _ptr(ws),
         b, d, l, n, g,
         u.stride(0), u.stride(1), delta.stride(0), delta.stride(1), dout.stride(0), dout.stride(1),
         du.stride(0), du.stride(1), ddelta.stride(0), ddelta.stride(1),
@@ -103,4 +104,4 @@ def selective_scan_bwd(u, delta, A, B, C_, D, delta_bias, dout, ckpt, delta_soft
         int(bool(delta_softplus)), _DT[u.dtype])
     with torch.cuda.device(u.device):
         _lib.check(L.vmb_selective_scan_bwd(C.byref(a), _stream(u)), "selective_scan_bwd")
-    return du, ddelta, dA, dB.to(B.dtype), dC.to(C_.dtype), dD, dbias
+    return du, ddelta, dA, dB, dC, dD, dbias
