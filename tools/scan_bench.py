@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--L", type=int, nargs="+", default=[4096])
     ap.add_argument("--dtypes", nargs="+", default=["bf16", "fp32"])
     ap.add_argument("--bwd", action="store_true")
+    ap.add_argument("--ref", action="store_true", help="also time the reference CUDA kernel rebuilt for sm_100a (oracle/_ref)")
     a = ap.parse_args()
     dev = "cuda"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -61,6 +62,17 @@ def main():
                         msb = bench(lambda: ops.selective_scan_bwd(u, delta, A, Bm, Cm, Dv, bias, dout, ck, True), flush=flush)
                         bb = B * (s * (5 * D * L + 4 * K * N * L))
                         rec.update(bwd_ms=round(msb, 4), bwd_us_per_img=round(msb * 1e3 / B, 3), bwd_GBps=round(bb / msb / 1e6, 1))
+                    if a.ref:
+                        import importlib.util
+                        so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "selective_scan_cuda_core.so")
+                        spec = importlib.util.spec_from_file_location("selective_scan_cuda_core", so)
+                        refm = importlib.util.module_from_spec(spec); spec.loader.exec_module(refm)
+                        msr = bench(lambda: refm.fwd(u, delta, A, Bm, Cm, Dv, bias, True, 1), flush=flush)
+                        rec.update(ref_ms=round(msr, 4), ref_us_per_img=round(msr * 1e3 / B, 3), speedup_vs_ref=round(msr / ms, 2))
+                        if a.bwd:
+                            o_r, x_r = refm.fwd(u, delta, A, Bm, Cm, Dv, bias, True, 1)
+                            msrb = bench(lambda: refm.bwd(u, delta, A, Bm, Cm, Dv, bias, dout, x_r, True, 1), flush=flush)
+                            rec.update(ref_bwd_ms=round(msrb, 4), bwd_speedup_vs_ref=round(msrb / msb, 2))
                     print(json.dumps(rec), flush=True)
 
 

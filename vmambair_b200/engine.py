@@ -1,0 +1,74 @@
+"""Public inference / training entry points around the drop-in networks.
+
+InferenceEngine: static-shape, CUDA-graph-replayed forward with pinned host staging -- the call a user
+makes to upscale a batch of LQ tiles (host tensor in, host tensor out).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+# parameters that stay fp32 when the network runs in bf16 (the scan keeps state/params in fp32,
+# reference: csrc/selective_scan/cus/selective_scan.cpp:165-172,203,211)
+_FP32_PARAMS = ("A_logs", "Ac_logs", "Ds", "Dsc", "dt_projs_bias", "dtc_projs_bias")
+
+
+def cast_for_inference(net: torch.nn.Module, dtype: torch.dtype) -> torch.nn.Module:
+    for name, p in net.named_parameters():
+        if name.rsplit(".", 1)[-1] in _FP32_PARAMS:
+            p.data = p.data.float()
+        else:
+            p.data = p.data.to(dtype)
+    return net
+
+
+class InferenceEngine:
+    def __init__(self, net: torch.nn.Module, batch: int, height: int, width: int, dtype=torch.bfloat16,
+                 device="cuda", in_channels: int = 3, use_graph: bool = True):
+        self.device = torch.device(device)
+        self.net = cast_for_inference(net.to(self.device).eval(), dtype)
+        self.dtype = dtype
+        self.x_dev = torch.zeros(batch, in_channels, height, width, device=self.device, dtype=dtype)
+        self.x_host = torch.zeros(batch, in_channels, height, width, dtype=dtype).pin_memory()
+        self.stream = torch.cuda.Stream(self.device)
+        self.graph = None
+        self.launches_per_step = 0
+        with torch.cuda.device(self.device), torch.no_grad():
+            with torch.cuda.stream(self.stream):
+                for _ in range(2):  # warm-up (cuDNN autotune, lazy module load) before capture
+                    y = self.net(self.x_dev)
+                n0 = ops.launch_count()
+                y = self.net(self.x_dev)
+                self.launches_per_step = ops.launch_count() - n0
+            self.stream.synchronize()
+            self.y_dev = y
+            if use_graph:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream):
+                    self.y_dev = self.net(self.x_dev)
+                self.graph = g
+        self.y_host = torch.empty(self.y_dev.shape, dtype=self.y_dev.dtype).pin_memory()
+
+    @torch.no_grad()
+    def step_device(self):
+        """one forward on the resident input (x_dev -> y_dev), on self.stream"""
+        with torch.cuda.stream(self.stream):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self.y_dev = self.net(self.x_dev)
+        return self.y_dev
+
+    @torch.no_grad()
+    def run(self, x_host: torch.Tensor) -> torch.Tensor:
+        """host (pinned or pageable) batch in -> host result out; H2D + forward + D2H on one stream."""
+        with torch.cuda.stream(self.stream):
+            self.x_dev.copy_(x_host, non_blocking=True)
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self.y_dev = self.net(self.x_dev)
+            self.y_host.copy_(self.y_dev, non_blocking=True)
+        self.stream.synchronize()
+        return self.y_host

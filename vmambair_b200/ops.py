@@ -16,6 +16,38 @@ from . import _lib
 _DT = {torch.float32: _lib.DT_F32, torch.bfloat16: _lib.DT_BF16, torch.float16: _lib.DT_F16}
 
 
+_LAUNCHES = 0          # kernels of this library launched so far (host-side count)
+_TIMING = None         # when a list: (tag, bytes, start_event, end_event) per library call (bench roofline)
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+def set_timing(records):
+    """records: None (off) or a list that receives (tag, algorithmic_bytes, start_event, end_event)."""
+    global _TIMING
+    _TIMING = records
+
+
+class _timed:
+    def __init__(self, tag, nbytes, dev, kernels):
+        self.tag, self.nbytes, self.dev, self.kernels = tag, nbytes, dev, kernels
+
+    def __enter__(self):
+        if _TIMING is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record(torch.cuda.current_stream(self.dev))
+
+    def __exit__(self, *a):
+        global _LAUNCHES
+        _LAUNCHES += self.kernels
+        if _TIMING is not None:
+            self.e.record(torch.cuda.current_stream(self.dev))
+            _TIMING.append((self.tag, self.nbytes, self.s, self.e))
+
+
 def _stream(t: torch.Tensor):
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
@@ -75,7 +107,9 @@ def selective_scan_fwd(u, delta, A, B, C_, D=None, delta_bias=None, delta_softpl
         u.stride(0), u.stride(1), delta.stride(0), delta.stride(1), out.stride(0), out.stride(1),
         B.stride(0), B.stride(1), B.stride(2), C_.stride(0), C_.stride(1), C_.stride(2),
         int(bool(delta_softplus)), _DT[u.dtype])
-    with torch.cuda.device(u.device):
+    es = u.element_size()
+    nbytes = es * (3 * b * d * l + 2 * b * g * n * l) + 4 * (d * n + 2 * d)  # every operand once
+    with torch.cuda.device(u.device), _timed("scan_fwd", nbytes, u.device, 1):
         _lib.check(L.vmb_selective_scan_fwd(C.byref(a), _stream(u)), "selective_scan_fwd")
     return out, ckpt
 
@@ -102,6 +136,8 @@ def selective_scan_bwd(u, delta, A, B, C_, D, delta_bias, dout, ckpt, delta_soft
         du.stride(0), du.stride(1), ddelta.stride(0), ddelta.stride(1),
         B.stride(0), B.stride(1), B.stride(2), C_.stride(0), C_.stride(1), C_.stride(2),
         int(bool(delta_softplus)), _DT[u.dtype])
-    with torch.cuda.device(u.device):
+    es = u.element_size()
+    nbytes = es * (5 * b * d * l + 4 * b * g * n * l) + 4 * b * d * ((l + 63) // 64) * n
+    with torch.cuda.device(u.device), _timed("scan_bwd", nbytes, u.device, 2):
         _lib.check(L.vmb_selective_scan_bwd(C.byref(a), _stream(u)), "selective_scan_bwd")
     return du, ddelta, dA, dB, dC, dD, dbias
