@@ -84,6 +84,69 @@ typedef struct {
 int vmb_selective_scan_bwd(const vmb_scan_bwd_args* a, void* stream);
 int64_t vmb_scan_bwd_workspace_bytes(int batch, int ngroups, int dstate, int seqlen);
 
+
+/* ---- B1 module boundary: fused stages of one OSS block (inference) -------------------------------
+ * These replace the un-fused PyTorch ops of SS2D_1 / MamberBlock / FeedForward
+ * (SRGAN/VmambaIR/archs/MambaSISR6_arch.py:166-218, 395-515).  Activations are NCHW, pixel-contiguous. */
+
+/* out[b,m,p] = epi( sum_k W[m,k] * pro(x)[b,k,p] ): 1x1 conv with fused LayerNorm / channel-gate prologue and
+ * bias / SiLU-range / residual epilogue.  Replaces norm1+in_conv (:487-489), x_proj (:409-410), gate+out_conv+
+ * residual (:494-498,:512), norm2+project_in (:213), project_out+residual (:217,:513). */
+typedef struct {
+    const void* x; const void* w; const float* bias; const void* residual; void* out;
+    const float* ln_w; const float* ln_b;   /* LayerNorm over K per pixel (ln_mode 1: WithBias, 2: BiasFree) */
+    const float* gate;                      /* (B,K) fp32: gate_mode 1: x*(1+g), 2: x+g */
+    int ln_mode, gate_mode;
+    int act_from, act_to;                   /* SiLU on output channels [act_from, act_to) */
+    int batch, K, M, P;
+    int64_t x_bs, x_cs, r_bs, r_cs, o_bs, o_cs, g_bs;
+    int64_t w_ld;                           /* row stride of w (0: = K); rows padded to a multiple of 16 elements load vectorised */
+    int dtype, out_dtype;                   /* x / w / residual dtype; out dtype (same, or VMB_F32) */
+} vmb_pixlin_args;
+int vmb_pixlin(const vmb_pixlin_args* a, void* stream);
+
+/* depthwise 3x3 (pad 1) + bias, then mode 0: SiLU (SS2D_1.conv2d+act :490-491) or mode 1: gelu(conv[c]) *
+ * conv[c+C_out] (FeedForward.dwconv + gate :215-216).  w: (channels, 9) fp32. */
+typedef struct {
+    const void* x; const float* w; const float* bias; void* out;
+    int batch, c_out, H, W, mode;
+    int64_t x_bs, x_cs, o_bs, o_cs;
+    int dtype;
+} vmb_dwconv_args;
+int vmb_dwconv3x3(const vmb_dwconv_args* a, void* stream);
+
+/* four scan orders by index arithmetic (cross_scan_2d :401-404; CrossScan RealSR arch :325-343):
+ * out[b][k][row][l] = src[k][b][row][pi_k(l)];  pi_0(l)=l, pi_1(w*H+h)=h*W+w, pi_2 = pi_0(L-1-l), pi_3 = pi_1(L-1-l). */
+typedef struct {
+    const void* src[4]; void* out;
+    int batch, rows, H, W;
+    int64_t src_bs, src_rs, out_bs;
+    int dtype;
+} vmb_cross_scan_args;
+int vmb_cross_scan(const vmb_cross_scan_args* a, void* stream);
+
+/* inverse orders + 4-way fp32 sum (:427-430 / CrossMerge) + out_norm (:433) + gate y*SiLU(z) (:493) +
+ * per-(b,c) sums of the result for AdaptiveAvgPool2d (:441; `pooled` fp32 (B,C), caller zero-fills). */
+typedef struct {
+    const void* ys; const void* z; const float* ln_w; const float* ln_b; void* y2; float* pooled;
+    int batch, C, H, W;
+    int64_t z_bs, z_cs;
+    int dtype;
+} vmb_merge_args;
+int vmb_merge_norm_gate(const vmb_merge_args* a, void* stream);
+
+/* the channel-direction OSS for one image per CTA (cforward_corev1 :438-483; Mamber32/33 and RealSR variants):
+ * pooled means -> conv_cin -> xc_proj / dtc_proj -> bidirectional selective scan over L=C -> conv_cout ->
+ * channel_norm.  All parameters fp32; c_out fp32 (B,C). cin_w / cout_w may be NULL (RealSR: dc=1). */
+typedef struct {
+    const float* pooled; float inv_count;
+    const float* cin_w; const float* cin_b; const float* xc_proj; const float* dtc_w; const float* dtc_b;
+    const float* Ac_logs; const float* Dsc; const float* cout_w; const float* cout_b; const float* cn_w; const float* cn_b;
+    float* c_out;
+    int batch, C, dc, Rc, N;
+} vmb_channel_args;
+int vmb_channel_branch(const vmb_channel_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

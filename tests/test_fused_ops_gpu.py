@@ -1,0 +1,144 @@
+"""Unit parity of each fused OSS-block stage (through the C-ABI) against the same op in plain fp32 torch."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+TOL = {torch.float32: (1e-4, 1e-4), torch.bfloat16: (3e-2, 3e-2), torch.float16: (4e-3, 4e-3)}
+
+
+def close(a, b, dtype, scale=1.0):
+    rtol, atol = TOL[dtype]
+    torch.testing.assert_close(a.float().cpu(), b.float().cpu(), rtol=rtol, atol=atol * scale)
+
+
+def ln_ref(x, w, b):
+    mu = x.mean(1, keepdim=True)
+    var = x.var(1, keepdim=True, unbiased=False)
+    y = (x - mu) / torch.sqrt(var + 1e-5) if b is not None else x / torch.sqrt(var + 1e-5)
+    y = y * w.view(1, -1, 1)
+    return y + b.view(1, -1, 1) if b is not None else y
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("K,M,P", [(48, 96, 256), (96, 140, 4096), (127, 48, 100), (384, 768, 64), (1021, 384, 64), (20, 17, 37)])
+def test_pixlin_plain(dtype, K, M, P):
+    from vmambair_b200 import ops
+    torch.manual_seed(K + M)
+    x = torch.randn(2, K, P, device="cuda").to(dtype)
+    w = (torch.randn(M, K, device="cuda") / K ** 0.5).to(dtype)
+    bias = torch.randn(M, device="cuda")
+    out = ops.pixlin(x, w, bias)
+    ref = torch.einsum("mk,bkp->bmp", w.float(), x.float()) + bias.view(1, -1, 1)
+    close(out, ref, dtype)
+    out32 = ops.pixlin(x, w, None, out_dtype=torch.float32)
+    assert out32.dtype == torch.float32
+    close(out32, ref - bias.view(1, -1, 1), dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("ln_mode", [1, 2])
+def test_pixlin_ln_act_residual_gate(dtype, ln_mode):
+    from vmambair_b200 import ops
+    torch.manual_seed(3)
+    B, K, M, P = 2, 96, 192, 320
+    x = (torch.randn(B, K, P, device="cuda") * 2 + 0.5).to(dtype)
+    w = (torch.randn(M, K, device="cuda") / K ** 0.5).to(dtype)
+    bias = torch.randn(M, device="cuda")
+    lw, lb = torch.rand(K, device="cuda") + 0.5, torch.randn(K, device="cuda") * 0.1
+    out = ops.pixlin(x, w, bias, ln=(ln_mode, lw, lb if ln_mode == 1 else None), act=(96, 192))
+    xn = ln_ref(x.float(), lw, lb if ln_mode == 1 else None)
+    if dtype != torch.float32:
+        xn = xn.to(dtype).float()
+    ref = torch.einsum("mk,bkp->bmp", w.float(), xn) + bias.view(1, -1, 1)
+    ref = torch.cat([ref[:, :96], F.silu(ref[:, 96:])], 1)
+    close(out, ref, dtype)
+    # gate prologue + residual epilogue on a strided (channel-offset) input view
+    big = torch.randn(B, 2 * K, P, device="cuda").to(dtype)
+    xv = big[:, K:]
+    res = torch.randn(B, M, P, device="cuda").to(dtype)
+    g = torch.randn(B, K, device="cuda")
+    for mode in (1, 2):
+        out = ops.pixlin(xv, w, bias, residual=res, gate=g, gate_mode=mode)
+        xg = xv.float() * (1 + g[:, :, None]) if mode == 1 else xv.float() + g[:, :, None]
+        if dtype != torch.float32:
+            xg = xg.to(dtype).float()
+        ref = torch.einsum("mk,bkp->bmp", w.float(), xg) + bias.view(1, -1, 1) + res.float()
+        close(out, ref, dtype, scale=4.0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("H,W", [(64, 64), (12, 8), (7, 9)])
+def test_dwconv_modes(dtype, H, W):
+    from vmambair_b200 import ops
+    torch.manual_seed(1)
+    B, C = 2, 10
+    x = torch.randn(B, 2 * C, H, W, device="cuda").to(dtype)
+    w = torch.randn(2 * C, 1, 3, 3, device="cuda") * 0.3
+    b = torch.randn(2 * C, device="cuda") * 0.1
+    conv = F.conv2d(x.float(), w, b, padding=1, groups=2 * C)
+    o0 = ops.dwconv3x3(x.view(B, 2 * C, H * W)[:, :C], w.view(-1, 9)[:C].contiguous(), b[:C].contiguous(), C, H, W, 0)
+    close(o0, F.silu(conv[:, :C]).flatten(2), dtype)
+    o1 = ops.dwconv3x3(x.view(B, 2 * C, H * W), w.view(-1, 9).contiguous(), b, C, H, W, 1)
+    close(o1, (F.gelu(conv[:, :C]) * conv[:, C:]).flatten(2), dtype, scale=2.0)
+    o2 = ops.dwconv3x3(x.view(B, 2 * C, H * W), w.view(-1, 9).contiguous(), None, C, H, W, 1)
+    conv_nb = F.conv2d(x.float(), w, None, padding=1, groups=2 * C)
+    close(o2, (F.gelu(conv_nb[:, :C]) * conv_nb[:, C:]).flatten(2), dtype, scale=2.0)
+
+
+@pytest.mark.parametrize("H,W", [(64, 64), (16, 24), (5, 3)])
+def test_cross_scan_bit_exact(H, W, golden_dir):
+    """the six-direction gather must be bit-exact (BASELINE.json): compare with the reference's index maps."""
+    from vmambair_b200 import ops
+    torch.manual_seed(0)
+    B, C = 2, 6
+    x = torch.randn(B, C, H, W, device="cuda")
+    xs = ops.cross_scan([x.view(B, C, H * W)] * 4, C, H, W)
+    rows, cols = x.flatten(2), x.transpose(2, 3).flatten(2)
+    ref = torch.stack([rows, cols, rows.flip(-1), cols.flip(-1)], 1)
+    assert torch.equal(xs, ref)
+    # distinct sources per direction (strided channel views of one tensor)
+    big = torch.randn(B, 4, C + 3, H * W, device="cuda")
+    out = ops.cross_scan([big[:, k, :C] for k in range(4)], C, H, W)
+    v = [big[:, k, :C].reshape(B, C, H, W) for k in range(4)]
+    ref = torch.stack([v[0].flatten(2), v[1].transpose(2, 3).flatten(2), v[2].flatten(2).flip(-1),
+                       v[3].transpose(2, 3).flatten(2).flip(-1)], 1)
+    assert torch.equal(out, ref)
+    xb = x.to(torch.bfloat16)
+    assert torch.equal(ops.cross_scan([xb.view(B, C, H * W)] * 4, C, H, W)[:, 1], xb.transpose(2, 3).flatten(2))
+
+
+def test_cross_scan_matches_reference_golden(golden_dir):
+    import os
+    import numpy as np
+    from vmambair_b200 import ops
+    z = np.load(os.path.join(golden_dir, "cross_scan.npz"))
+    x = torch.from_numpy(z["x"]).cuda()
+    B, C, H, W = x.shape
+    xs = ops.cross_scan([x.view(B, C, H * W)] * 4, C, H, W)
+    assert torch.equal(xs.cpu(), torch.from_numpy(z["xs"]))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C,H,W", [(48, 16, 24), (96, 64, 64), (32, 5, 7)])
+def test_merge_norm_gate(dtype, C, H, W):
+    from vmambair_b200 import ops
+    torch.manual_seed(2)
+    B, L = 2, H * W
+    ys = torch.randn(B, 4, C, L, device="cuda").to(dtype)
+    zbig = torch.randn(B, 2 * C, L, device="cuda").to(dtype)
+    z = zbig[:, C:]
+    lw, lb = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda") * 0.1
+    y2, pooled = ops.merge_norm_gate(ys, z, lw, lb, C, H, W)
+    f = ys.float()
+    y = f[:, 0] + f[:, 2].flip(-1) + f[:, 1].view(B, C, W, H).transpose(2, 3).reshape(B, C, L) \
+        + f[:, 3].flip(-1).view(B, C, W, H).transpose(2, 3).reshape(B, C, L)
+    yn = ln_ref(y, lw, lb)
+    if dtype != torch.float32:
+        yn = yn.to(dtype).float()
+    ref = yn * z.float()
+    close(y2, ref, dtype, scale=2.0)
+    torch.testing.assert_close(pooled.cpu(), y2.float().sum(-1).cpu(), rtol=2e-3, atol=2e-2)

@@ -41,6 +41,49 @@ class ScanBwdArgs(C.Structure):
     ]
 
 
+class PixlinArgs(C.Structure):
+    _fields_ = [
+        ("x", vp), ("w", vp), ("bias", vp), ("residual", vp), ("out", vp), ("ln_w", vp), ("ln_b", vp), ("gate", vp),
+        ("ln_mode", C.c_int), ("gate_mode", C.c_int), ("act_from", C.c_int), ("act_to", C.c_int),
+        ("batch", C.c_int), ("K", C.c_int), ("M", C.c_int), ("P", C.c_int),
+        ("x_bs", i64), ("x_cs", i64), ("r_bs", i64), ("r_cs", i64), ("o_bs", i64), ("o_cs", i64), ("g_bs", i64), ("w_ld", i64),
+        ("dtype", C.c_int), ("out_dtype", C.c_int),
+    ]
+
+
+class DwconvArgs(C.Structure):
+    _fields_ = [
+        ("x", vp), ("w", vp), ("bias", vp), ("out", vp),
+        ("batch", C.c_int), ("c_out", C.c_int), ("H", C.c_int), ("W", C.c_int), ("mode", C.c_int),
+        ("x_bs", i64), ("x_cs", i64), ("o_bs", i64), ("o_cs", i64), ("dtype", C.c_int),
+    ]
+
+
+class CrossScanArgs(C.Structure):
+    _fields_ = [
+        ("src", vp * 4), ("out", vp),
+        ("batch", C.c_int), ("rows", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("src_bs", i64), ("src_rs", i64), ("out_bs", i64), ("dtype", C.c_int),
+    ]
+
+
+class MergeArgs(C.Structure):
+    _fields_ = [
+        ("ys", vp), ("z", vp), ("ln_w", vp), ("ln_b", vp), ("y2", vp), ("pooled", vp),
+        ("batch", C.c_int), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("z_bs", i64), ("z_cs", i64), ("dtype", C.c_int),
+    ]
+
+
+class ChannelArgs(C.Structure):
+    _fields_ = [
+        ("pooled", vp), ("inv_count", C.c_float),
+        ("cin_w", vp), ("cin_b", vp), ("xc_proj", vp), ("dtc_w", vp), ("dtc_b", vp), ("Ac_logs", vp), ("Dsc", vp),
+        ("cout_w", vp), ("cout_b", vp), ("cn_w", vp), ("cn_b", vp), ("c_out", vp),
+        ("batch", C.c_int), ("C", C.c_int), ("dc", C.c_int), ("Rc", C.c_int), ("N", C.c_int),
+    ]
+
+
 # every symbol include/vmambair_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "vmb_last_error": (C.c_char_p, []),
@@ -49,6 +92,11 @@ SYMBOLS = {
     "vmb_selective_scan_fwd": (C.c_int, [C.POINTER(ScanFwdArgs), vp]),
     "vmb_selective_scan_bwd": (C.c_int, [C.POINTER(ScanBwdArgs), vp]),
     "vmb_scan_bwd_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vmb_pixlin": (C.c_int, [C.POINTER(PixlinArgs), vp]),
+    "vmb_dwconv3x3": (C.c_int, [C.POINTER(DwconvArgs), vp]),
+    "vmb_cross_scan": (C.c_int, [C.POINTER(CrossScanArgs), vp]),
+    "vmb_merge_norm_gate": (C.c_int, [C.POINTER(MergeArgs), vp]),
+    "vmb_channel_branch": (C.c_int, [C.POINTER(ChannelArgs), vp]),
 }
 
 

@@ -4,6 +4,7 @@
 
 #include "common.cuh"
 #include "scan_params.h"
+#include "oss_params.h"
 
 namespace vmb {
 static thread_local char g_err[512] = "";
@@ -94,4 +95,66 @@ extern "C" int vmb_selective_scan_bwd(const vmb_scan_bwd_args* a, void* stream) 
                mult(a->ddelta_bs) && mult(a->ddelta_ds) && mult(a->B_bs) && mult(a->B_gs) && mult(a->B_ns) &&
                mult(a->C_bs) && mult(a->C_gs) && mult(a->C_ns);
     return scan_bwd_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
+}
+
+static inline bool dt_ok(int d) { return d == VMB_F32 || d == VMB_BF16 || d == VMB_F16; }
+
+extern "C" int vmb_pixlin(const vmb_pixlin_args* a, void* stream) {
+    VMB_CHECK(a && a->x && a->w && a->out, "pixlin: null pointer");
+    VMB_CHECK(dt_ok(a->dtype) && (a->out_dtype == a->dtype || a->out_dtype == VMB_F32), "pixlin: bad dtype");
+    VMB_CHECK(a->batch > 0 && a->batch <= 65535 && a->K > 0 && a->M > 0 && a->P > 0, "pixlin: bad sizes");
+    VMB_CHECK(a->ln_mode == 0 || a->ln_w, "pixlin: ln_w missing");
+    VMB_CHECK(a->ln_mode != 1 || a->ln_b, "pixlin: ln_b missing");
+    VMB_CHECK(a->gate_mode == 0 || a->gate, "pixlin: gate missing");
+    PixlinParams p{a->x, a->w, a->bias, a->residual, a->out, a->ln_w, a->ln_b, a->gate, a->ln_mode, a->gate_mode,
+                   a->act_from, a->act_to, a->batch, a->K, a->M, a->P, a->x_bs, a->x_cs, a->r_bs, a->r_cs, a->o_bs, a->o_cs,
+                   a->g_bs, a->w_ld > 0 ? a->w_ld : a->K, false, false};
+    {
+        const int vw = 16 / elt_size(a->dtype);
+        const int64_t kpad = (a->K + 15) / 16 * 16;
+        p.w_vec = aligned16(a->w) && p.w_ld % vw == 0 && p.w_ld >= kpad;
+    }
+    const int v = 16 / elt_size(a->dtype), vo = 16 / elt_size(a->out_dtype);
+    const int vm = v > vo ? v : vo;
+    auto mult = [vm](int64_t s) { return s % vm == 0; };
+    p.vec_ok = aligned16(a->x) && aligned16(a->out) && (!a->residual || aligned16(a->residual)) && mult(a->x_bs) &&
+               mult(a->x_cs) && mult(a->o_bs) && mult(a->o_cs) && (!a->residual || (mult(a->r_bs) && mult(a->r_cs))) &&
+               a->P % vm == 0;
+    return pixlin_launch(p, a->dtype, a->out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vmb_dwconv3x3(const vmb_dwconv_args* a, void* stream) {
+    VMB_CHECK(a && a->x && a->w && a->out, "dwconv: null pointer");
+    VMB_CHECK(dt_ok(a->dtype), "dwconv: bad dtype");
+    VMB_CHECK(a->batch > 0 && a->c_out > 0 && a->H > 0 && a->W > 0 && (long)a->batch * a->c_out <= 65535, "dwconv: bad sizes");
+    DwParams p{a->x, a->w, a->bias, a->out, a->batch, a->c_out, a->H, a->W, a->mode, a->x_bs, a->x_cs, a->o_bs, a->o_cs, false};
+    p.vec_ok = a->W % 8 == 0 && aligned16(a->x) && aligned16(a->out) && a->x_bs % 8 == 0 && a->x_cs % 8 == 0 &&
+               a->o_bs % 8 == 0 && a->o_cs % 8 == 0;
+    return dwconv_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vmb_cross_scan(const vmb_cross_scan_args* a, void* stream) {
+    VMB_CHECK(a && a->src[0] && a->src[1] && a->src[2] && a->src[3] && a->out, "cross_scan: null pointer");
+    VMB_CHECK(dt_ok(a->dtype), "cross_scan: bad dtype");
+    CrossScanParams p{{a->src[0], a->src[1], a->src[2], a->src[3]}, a->out, a->batch, a->rows, a->H, a->W, a->src_bs,
+                      a->src_rs, a->out_bs};
+    return cross_scan_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vmb_merge_norm_gate(const vmb_merge_args* a, void* stream) {
+    VMB_CHECK(a && a->ys && a->z && a->ln_w && a->ln_b && a->y2 && a->pooled, "merge: null pointer");
+    VMB_CHECK(dt_ok(a->dtype), "merge: bad dtype");
+    VMB_CHECK(a->batch > 0 && a->batch <= 65535, "merge: bad batch");
+    MergeParams p{a->ys, a->z, a->ln_w, a->ln_b, a->y2, a->pooled, a->batch, a->C, a->H, a->W, a->z_bs, a->z_cs};
+    return merge_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vmb_channel_branch(const vmb_channel_args* a, void* stream) {
+    VMB_CHECK(a && a->pooled && a->xc_proj && a->dtc_w && a->dtc_b && a->Ac_logs && a->Dsc && a->cn_w && a->cn_b && a->c_out,
+              "channel_branch: null pointer");
+    VMB_CHECK((a->cin_w == nullptr) == (a->cin_b == nullptr) && (a->cout_w == nullptr) == (a->cout_b == nullptr),
+              "channel_branch: conv_cin / conv_cout weight and bias must come together");
+    ChannelParams p{a->pooled, a->inv_count, a->cin_w, a->cin_b, a->xc_proj, a->dtc_w, a->dtc_b, a->Ac_logs, a->Dsc,
+                    a->cout_w, a->cout_b, a->cn_w, a->cn_b, a->c_out, a->batch, a->C, a->dc, a->Rc, a->N};
+    return channel_launch(p, static_cast<cudaStream_t>(stream));
 }

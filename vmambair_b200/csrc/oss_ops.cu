@@ -1,0 +1,368 @@
+// Memory-bound stages of the fused OSS block (reference: SRGAN/VmambaIR/archs/MambaSISR6_arch.py):
+//   dwconv3x3_kernel       depthwise 3x3 + bias + SiLU (SS2D_1.conv2d/act :286-294,490-491) or the EFFN's
+//                          depthwise 3x3 + exact-GELU gate (FeedForward :215-216)
+//   cross_scan_kernel      the four direction orders as index arithmetic (cross_scan_2d :401-404 / CrossScan):
+//                          out[k][row][l] = src_k[row][pi_k(l)],  pi_0 = id, pi_1 = column-major, pi_2/3 = reversed
+//   merge_norm_gate_kernel inverse orders + 4-way sum in the reference's fp32 order (:427-430), out_norm
+//                          LayerNorm over C (:433), gate with SiLU(z) (:493) and the per-(b,c) pooled sums
+//                          for the channel branch (AdaptiveAvgPool2d, :441)
+//   channel_branch_kernel  the whole channel OSS (cforward_corev1 :438-483 and the 3 other variants) for one
+//                          image in one CTA: conv_cin, xc_proj, dtc_proj, bidirectional scan over L=C,
+//                          conv_cout, channel_norm -> c[b][C]
+#include "common.cuh"
+#include "oss_params.h"
+
+namespace vmb {
+
+__device__ __forceinline__ float silu2(float v) { return v * rcp_approx(1.f + ex2(-v * kLog2e)); }
+__device__ __forceinline__ float gelu_exact(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
+
+// ------------------------------------------------------------------------------------------ depthwise 3x3
+
+template <typename in_t>
+__device__ __forceinline__ float dw_at(const in_t* __restrict__ xc, const float* __restrict__ w9, int h, int w, int H, int W) {
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int hh = h + dy;
+        if (hh < 0 || hh >= H) continue;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int ww = w + dx;
+            if (ww < 0 || ww >= W) continue;
+            acc = fmaf(w9[(dy + 1) * 3 + dx + 1], to_f32<in_t>(xc[hh * W + ww]), acc);
+        }
+    }
+    return acc;
+}
+
+// strip version: one thread = 8 consecutive pixels of one row (16 B vector loads of the 3 input rows + 2 halo scalars)
+template <typename in_t>
+__device__ __forceinline__ void dw_strip(const in_t* __restrict__ xc, const float* __restrict__ w9, int h, int w0, int H, int W,
+                                         float bias, float* acc) {
+    constexpr int V = Vec<in_t>::N;  // 8 (16-bit) or 4 (fp32): two vectors for fp32
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = bias;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int hh = h + dy;
+        if (hh < 0 || hh >= H) continue;
+        const in_t* __restrict__ row = xc + (int64_t)hh * W;
+        float v[10];
+        v[0] = w0 > 0 ? to_f32<in_t>(row[w0 - 1]) : 0.f;
+        v[9] = w0 + 8 < W ? to_f32<in_t>(row[w0 + 8]) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8 / V; ++j) load_vec<in_t>(row + w0 + j * V, v + 1 + j * V, V, true);
+        const float k0 = w9[(dy + 1) * 3], k1 = w9[(dy + 1) * 3 + 1], k2 = w9[(dy + 1) * 3 + 2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(k2, v[i + 2], fmaf(k1, v[i + 1], fmaf(k0, v[i], acc[i])));
+    }
+}
+
+template <typename in_t>
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwParams p) {
+    const int c = blockIdx.y % p.Cout, b = blockIdx.y / p.Cout;
+    const int L = p.H * p.W;
+    const in_t* __restrict__ xb = reinterpret_cast<const in_t*>(p.x) + (int64_t)b * p.x_bs;
+    in_t* __restrict__ ob = reinterpret_cast<in_t*>(p.out) + (int64_t)b * p.o_bs + (int64_t)c * p.o_cs;
+    float w0[9], w1[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        w0[i] = p.w[c * 9 + i];
+        w1[i] = p.mode ? p.w[(c + p.Cout) * 9 + i] : 0.f;
+    }
+    const float b0 = p.bias ? p.bias[c] : 0.f, b1 = (p.bias && p.mode) ? p.bias[c + p.Cout] : 0.f;
+    if (p.vec_ok) {
+        constexpr int V = Vec<in_t>::N;
+        for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 8; i < L; i += gridDim.x * blockDim.x * 8) {
+            const int h = i / p.W, w = i % p.W;
+            float a0[8], a1[8];
+            dw_strip<in_t>(xb + (int64_t)c * p.x_cs, w0, h, w, p.H, p.W, b0, a0);
+            if (p.mode == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a0[j] = silu2(a0[j]);
+            } else {
+                dw_strip<in_t>(xb + (int64_t)(c + p.Cout) * p.x_cs, w1, h, w, p.H, p.W, b1, a1);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a0[j] = gelu_exact(a0[j]) * a1[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8 / V; ++j) store_vec<in_t>(ob + i + j * V, a0 + j * V, V, true);
+        }
+        return;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
+        const int h = i / p.W, w = i % p.W;
+        float v = dw_at<in_t>(xb + (int64_t)c * p.x_cs, w0, h, w, p.H, p.W) + b0;
+        if (p.mode == 0) {
+            v = silu2(v);
+        } else {
+            const float g = dw_at<in_t>(xb + (int64_t)(c + p.Cout) * p.x_cs, w1, h, w, p.H, p.W) + b1;
+            v = gelu_exact(v) * g;
+        }
+        ob[i] = from_f32<in_t>(v);
+    }
+}
+
+int dwconv_launch(const DwParams& p, int dtype, cudaStream_t stream) {
+    const int L = p.H * p.W;
+    const int per_thread = p.vec_ok ? 8 : 1;
+    dim3 grid((L / per_thread + 255) / 256 > 0 ? (L / per_thread + 255) / 256 : 1, p.B * p.Cout);
+    switch (dtype) {
+        case VMB_F32: dwconv3x3_kernel<float><<<grid, 256, 0, stream>>>(p); break;
+        case VMB_BF16: dwconv3x3_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(p); break;
+        case VMB_F16: dwconv3x3_kernel<__half><<<grid, 256, 0, stream>>>(p); break;
+        default: set_error("dwconv: unsupported dtype %d", dtype); return VMB_ERR_INVALID;
+    }
+    VMB_CUDA(cudaGetLastError());
+    return VMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ cross scan (4 orders)
+// One CTA = one (b, row-set entry, 32x32 pixel tile).  src rows may differ per direction (x_proj outputs) or be
+// shared (x).  Output row index = k*rows + row, sequence-contiguous.
+
+template <typename in_t>
+__global__ void __launch_bounds__(256) cross_scan_kernel(const CrossScanParams p) {
+    __shared__ float tile[4][32][33];
+    const int tiles_w = (p.W + 31) / 32;
+    const int th = blockIdx.x / tiles_w, tw = blockIdx.x % tiles_w;
+    const int row = blockIdx.y, b = blockIdx.z;
+    const int L = p.H * p.W;
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;  // 32 x 8
+    const int h0 = th * 32, w0 = tw * 32;
+    bool same = p.src[0] == p.src[1] && p.src[0] == p.src[2] && p.src[0] == p.src[3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (same && k > 0) break;
+        const in_t* __restrict__ s = reinterpret_cast<const in_t*>(p.src[k]) + (int64_t)b * p.src_bs + (int64_t)row * p.src_rs;
+        for (int j = ty; j < 32; j += 8) {
+            const int h = h0 + j, w = w0 + tx;
+            tile[k][j][tx] = (h < p.H && w < p.W) ? to_f32<in_t>(s[h * p.W + w]) : 0.f;
+        }
+    }
+    __syncthreads();
+    in_t* __restrict__ o = reinterpret_cast<in_t*>(p.out) + (int64_t)b * p.out_bs;
+    const int64_t dir_stride = (int64_t)p.rows * L;
+    for (int j = ty; j < 32; j += 8) {
+        // row-major orders: l = h*W + w (k=0) and its reversal (k=2); threads along w
+        int h = h0 + j, w = w0 + tx;
+        if (h < p.H && w < p.W) {
+            const int l = h * p.W + w;
+            o[0 * dir_stride + (int64_t)row * L + l] = from_f32<in_t>(tile[0][j][tx]);
+            o[2 * dir_stride + (int64_t)row * L + (L - 1 - l)] = from_f32<in_t>(tile[same ? 0 : 2][j][tx]);
+        }
+        // column-major orders: l = w*H + h (k=1) and its reversal (k=3); threads along h
+        h = h0 + tx;
+        w = w0 + j;
+        if (h < p.H && w < p.W) {
+            const int l = w * p.H + h;
+            o[1 * dir_stride + (int64_t)row * L + l] = from_f32<in_t>(tile[same ? 0 : 1][tx][j]);
+            o[3 * dir_stride + (int64_t)row * L + (L - 1 - l)] = from_f32<in_t>(tile[same ? 0 : 3][tx][j]);
+        }
+    }
+}
+
+int cross_scan_launch(const CrossScanParams& p, int dtype, cudaStream_t stream) {
+    dim3 grid(((p.H + 31) / 32) * ((p.W + 31) / 32), p.rows, p.B);
+    VMB_CHECK(p.rows <= 65535 && p.B <= 65535, "cross_scan: too many rows / batch");
+    switch (dtype) {
+        case VMB_F32: cross_scan_kernel<float><<<grid, 256, 0, stream>>>(p); break;
+        case VMB_BF16: cross_scan_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(p); break;
+        case VMB_F16: cross_scan_kernel<__half><<<grid, 256, 0, stream>>>(p); break;
+        default: set_error("cross_scan: unsupported dtype %d", dtype); return VMB_ERR_INVALID;
+    }
+    VMB_CUDA(cudaGetLastError());
+    return VMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ merge + out_norm + gate + pool
+// CTA = (b, 8x8 pixel tile), all C channels.  Phase 1: sum the four directions in the reference's order,
+// (y0 + flip(y2)) + T(y1) + T(flip(y3)), fp32, into smem [C][64].  Phase 2: LayerNorm over C per pixel,
+// * z, store y2, accumulate the per-channel sum of y2 (for AdaptiveAvgPool2d).
+
+template <typename in_t>
+__global__ void __launch_bounds__(256) merge_norm_gate_kernel(const MergeParams p) {
+    extern __shared__ float sm[];  // [C][65] + stats [2][64]
+    const int C = p.C, L = p.H * p.W;
+    float* sY = sm;
+    float* sMu = sm + C * 65;
+    float* sRs = sMu + 64;
+    const int tiles_w = (p.W + 7) / 8;
+    const int h0 = (blockIdx.x / tiles_w) * 8, w0 = (blockIdx.x % tiles_w) * 8;
+    const int b = blockIdx.y;
+    const in_t* __restrict__ ys = reinterpret_cast<const in_t*>(p.ys) + (int64_t)b * 4 * C * L;
+    const int q = threadIdx.x % 64;          // pixel in tile
+    const int ph = h0 + q / 8, pw = w0 + q % 8;
+    const bool ok = ph < p.H && pw < p.W;
+    const int l_row = ph * p.W + pw, l_col = pw * p.H + ph;
+    for (int c = threadIdx.x / 64; c < C; c += 4) {
+        float v = 0.f;
+        if (ok) {
+            const in_t* __restrict__ yc = ys + (int64_t)c * L;
+            const float y0 = to_f32<in_t>(yc[l_row]);
+            const float y2 = to_f32<in_t>(yc[(int64_t)2 * C * L + (L - 1 - l_row)]);
+            const float y1 = to_f32<in_t>(yc[(int64_t)1 * C * L + l_col]);
+            const float y3 = to_f32<in_t>(yc[(int64_t)3 * C * L + (L - 1 - l_col)]);
+            v = ((y0 + y2) + y1) + y3;
+        }
+        sY[c * 65 + q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float s = 0.f;
+        for (int c = 0; c < C; ++c) s += sY[c * 65 + threadIdx.x];
+        const float mu = s / C;
+        float v = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float d = sY[c * 65 + threadIdx.x] - mu;
+            v += d * d;
+        }
+        sMu[threadIdx.x] = mu;
+        sRs[threadIdx.x] = rsqrtf(v / C + 1e-5f);
+    }
+    __syncthreads();
+    const in_t* __restrict__ zb = reinterpret_cast<const in_t*>(p.z) + (int64_t)b * p.z_bs;
+    in_t* __restrict__ ob = reinterpret_cast<in_t*>(p.y2) + (int64_t)b * C * L;
+    for (int c = threadIdx.x / 64; c < C; c += 4) {
+        float v = 0.f;
+        if (ok) {
+            const float n = (sY[c * 65 + q] - sMu[q]) * sRs[q] * p.ln_w[c] + p.ln_b[c];
+            // the reference rounds y1 to the activation dtype before the gate (.to(x.dtype), :434)
+            const float n_r = to_f32<in_t>(from_f32<in_t>(n));
+            v = to_f32<in_t>(from_f32<in_t>(n_r * to_f32<in_t>(zb[(int64_t)c * p.z_cs + l_row])));
+            ob[(int64_t)c * L + l_row] = from_f32<in_t>(v);
+        }
+        // pooled sum over the 64 pixels of this tile (two warps per channel pass)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(p.pooled + (int64_t)b * C + c, v);
+    }
+}
+
+int merge_launch(const MergeParams& p, int dtype, cudaStream_t stream) {
+    dim3 grid(((p.H + 7) / 8) * ((p.W + 7) / 8), p.B);
+    const size_t smem = sizeof(float) * ((size_t)p.C * 65 + 128);
+    VMB_CHECK(smem <= 227 * 1024, "merge: C=%d too large", p.C);
+#define VMB_MERGE(T)                                                                                           \
+    {                                                                                                          \
+        auto k = merge_norm_gate_kernel<T>;                                                                    \
+        if (smem > 48 * 1024) VMB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k<<<grid, 256, smem, stream>>>(p);                                                                     \
+    }
+    switch (dtype) {
+        case VMB_F32: VMB_MERGE(float) break;
+        case VMB_BF16: VMB_MERGE(__nv_bfloat16) break;
+        case VMB_F16: VMB_MERGE(__half) break;
+        default: set_error("merge: unsupported dtype %d", dtype); return VMB_ERR_INVALID;
+    }
+#undef VMB_MERGE
+    VMB_CUDA(cudaGetLastError());
+    return VMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ channel branch
+// One CTA (256 threads) per image.  Sequence = the C pooled channel means, dc rows, 2 directions, N states.
+
+__global__ void __launch_bounds__(256) channel_branch_kernel(const ChannelParams p) {
+    extern __shared__ float sm[];
+    const int C = p.C, dc = p.dc, Rc = p.Rc, N = p.N, RN = Rc + 2 * N;
+    float* sSeq = sm;                    // [dc][C]     xc
+    float* sDbl = sSeq + dc * C;         // [2][RN][C]  xc_dbl per direction (direction order)
+    float* sDt = sDbl + 2 * RN * C;      // [2][dc][C]  softplus'ed dt
+    float* sY = sDt + 2 * dc * C;        // [2][dc][C]  scan outputs (direction order)
+    float* sOut = sY + 2 * dc * C;       // [C]
+    float* sRed = sOut + C;              // [64]
+    const int b = blockIdx.x, tid = threadIdx.x;
+    // xc = conv_cin(pool)  (per-channel affine of the pooled mean)
+    for (int i = tid; i < dc * C; i += 256) {
+        const int j = i / C, l = i % C;
+        const float m = p.pooled[(int64_t)b * C + l] * p.inv_count;
+        sSeq[i] = p.cin_w ? fmaf(m, p.cin_w[j], p.cin_b[j]) : m;
+    }
+    __syncthreads();
+    // xc_dbl[k][c][l] = sum_j W[k][c][j] * xs[k][j][l],  xs[1] = flipped sequence
+    for (int i = tid; i < 2 * RN * C; i += 256) {
+        const int k = i / (RN * C), c = (i / C) % RN, l = i % C;
+        const int ls = k ? C - 1 - l : l;
+        float a = 0.f;
+        for (int j = 0; j < dc; ++j) a = fmaf(p.xc_proj[(k * RN + c) * dc + j], sSeq[j * C + ls], a);
+        sDbl[i] = a;
+    }
+    __syncthreads();
+    // dt[k][j][l] = softplus(sum_r Wdt[k][j][r] * dbl[k][r][l] + bias)
+    for (int i = tid; i < 2 * dc * C; i += 256) {
+        const int k = i / (dc * C), j = (i / C) % dc, l = i % C;
+        float a = p.dtc_b[k * dc + j];
+        for (int r = 0; r < Rc; ++r) a = fmaf(p.dtc_w[(k * dc + j) * Rc + r], sDbl[(k * RN + r) * C + l], a);
+        sDt[i] = softplus_f(a);
+    }
+    __syncthreads();
+    // sequential scan: one thread per (direction k, row j, state n); N <= 16 lanes reduce y with shuffles
+    const int rows = 2 * dc;
+    const int unit = tid / 16, n = tid % 16;  // 16 units of 16 lanes
+    for (int row = unit; row < rows; row += 16) {
+        const int k = row / dc, j = row % dc;
+        const bool act = n < N;
+        const float A = act ? -__expf(p.Ac_logs[row * N + n]) * kLog2e : 0.f;
+        const float Dv = p.Dsc[row];
+        float h = 0.f;
+        for (int l = 0; l < C; ++l) {
+            const int ls = k ? C - 1 - l : l;
+            const float dt = sDt[(k * dc + j) * C + l];
+            const float u = sSeq[j * C + ls];
+            const float Bv = act ? sDbl[(k * RN + Rc + n) * C + l] : 0.f;
+            const float Cv = act ? sDbl[(k * RN + Rc + N + n) * C + l] : 0.f;
+            h = fmaf(ex2(dt * A), h, dt * u * Bv);
+            float y = h * Cv;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o, 16);
+            if (n == 0) sY[(k * dc + j) * C + l] = fmaf(Dv, u, y);
+        }
+    }
+    __syncthreads();
+    // merge directions, conv_cout, channel_norm over the C positions
+    float part = 0.f;
+    for (int l = tid; l < C; l += 256) {
+        float acc = p.cout_w ? p.cout_b[0] : 0.f;
+        for (int j = 0; j < dc; ++j) {
+            const float y = sY[(0 * dc + j) * C + l] + sY[(1 * dc + j) * C + (C - 1 - l)];
+            acc = p.cout_w ? fmaf(y, p.cout_w[j], acc) : acc + y;
+        }
+        sOut[l] = acc;
+        part += acc;
+    }
+    // block mean / variance (two-pass)
+    auto block_sum = [&](float v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((tid & 31) == 0) sRed[tid >> 5] = v;
+        __syncthreads();
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += sRed[i];
+        return t;
+    };
+    const float mu = block_sum(part) / C;
+    float vp = 0.f;
+    for (int l = tid; l < C; l += 256) {
+        const float d = sOut[l] - mu;
+        vp += d * d;
+    }
+    const float rstd = rsqrtf(block_sum(vp) / C + 1e-5f);
+    for (int l = tid; l < C; l += 256) p.c_out[(int64_t)b * C + l] = (sOut[l] - mu) * rstd * p.cn_w[l] + p.cn_b[l];
+}
+
+int channel_launch(const ChannelParams& p, cudaStream_t stream) {
+    VMB_CHECK(p.N <= 16, "channel branch: dstate <= 16 supported (got %d)", p.N);
+    const int RN = p.Rc + 2 * p.N;
+    const size_t smem = sizeof(float) * ((size_t)p.dc * p.C + 2 * RN * p.C + 4 * p.dc * p.C + p.C + 64);
+    VMB_CHECK(smem <= 227 * 1024, "channel branch: C=%d too large", p.C);
+    if (smem > 48 * 1024)
+        VMB_CUDA(cudaFuncSetAttribute(channel_branch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    channel_branch_kernel<<<p.B, 256, smem, stream>>>(p);
+    VMB_CUDA(cudaGetLastError());
+    return VMB_OK;
+}
+
+}  // namespace vmb

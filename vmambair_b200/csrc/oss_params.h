@@ -1,0 +1,43 @@
+// Internal parameter blocks of the fused OSS-block stages (see include/vmambair_b200.h for the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vmb {
+struct PixlinParams {
+    const void* x; const void* w; const float* bias; const void* residual; void* out;
+    const float* ln_w; const float* ln_b; const float* gate;
+    int ln_mode, gate_mode, act_from, act_to, B, K, M, P;
+    int64_t x_bs, x_cs, r_bs, r_cs, o_bs, o_cs, g_bs, w_ld;
+    bool vec_ok, w_vec;
+};
+struct DwParams {
+    const void* x; const float* w; const float* bias; void* out;
+    int B, Cout, H, W, mode;
+    int64_t x_bs, x_cs, o_bs, o_cs;
+    bool vec_ok;  // W % 8 == 0 and 16 B aligned rows: 8-pixel strips
+};
+struct CrossScanParams {
+    const void* src[4]; void* out;
+    int B, rows, H, W;
+    int64_t src_bs, src_rs, out_bs;
+};
+struct MergeParams {
+    const void* ys; const void* z; const float* ln_w; const float* ln_b; void* y2; float* pooled;
+    int B, C, H, W;
+    int64_t z_bs, z_cs;
+};
+struct ChannelParams {
+    const float* pooled; float inv_count;
+    const float* cin_w; const float* cin_b; const float* xc_proj; const float* dtc_w; const float* dtc_b;
+    const float* Ac_logs; const float* Dsc; const float* cout_w; const float* cout_b; const float* cn_w; const float* cn_b;
+    float* c_out;
+    int B, C, dc, Rc, N;
+};
+int pixlin_launch(const PixlinParams& p, int dtype, int out_dtype, cudaStream_t stream);
+int dwconv_launch(const DwParams& p, int dtype, cudaStream_t stream);
+int cross_scan_launch(const CrossScanParams& p, int dtype, cudaStream_t stream);
+int merge_launch(const MergeParams& p, int dtype, cudaStream_t stream);
+int channel_launch(const ChannelParams& p, cudaStream_t stream);
+}  // namespace vmb
+

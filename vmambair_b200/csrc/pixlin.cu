@@ -1,0 +1,326 @@
+// Per-pixel linear layer on NCHW activations ("1x1 conv") with fused prologue / epilogue:
+//     out[b, m, p] = epi( sum_k W[m,k] * pro(x)[b, k, p] )
+// replaces, inside one OSS block (reference SRGAN/VmambaIR/archs/MambaSISR6_arch.py):
+//   norm1 + in_conv (+SiLU on the z half)        :166-195, :487-489       (prologue LN, epilogue bias + SiLU range)
+//   x_proj for the 4 directions as ONE GEMM        :409-410                 (fp32 output)
+//   channel gate + out_conv + residual             :494-498, :512           (prologue per-(b,k) gate, epilogue residual)
+//   norm2 + project_in                             :213-214, :513           (prologue LN)
+//   project_out + residual                         :217, :513               (epilogue residual)
+// bf16/fp16 I/O: tensor cores (mma.sync m16n8k16, fp32 accumulate) on smem tiles;  fp32 I/O: FFMA tiles
+// (the fp32 mode exists for 1e-3 parity against the reference, not for speed).
+// Tile: 64 pixels x 64 output channels per step, the whole K (<=512) of the pixel tile resident in smem so the
+// LayerNorm statistics are computed once in the prologue; larger K streams in chunks of 512.
+#include "common.cuh"
+#include "oss_params.h"
+
+namespace vmb {
+
+constexpr int PL_PT = 64;      // pixels per CTA
+constexpr int PL_MT = 64;      // output channels per step
+constexpr int PL_KC = 512;     // resident K chunk
+constexpr int PL_THREADS = 128;
+
+template <typename T> struct MmaType;
+template <> struct MmaType<__nv_bfloat16> {
+    __device__ static void mma(float* c, const uint32_t* a, const uint32_t* b) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+};
+template <> struct MmaType<__half> {
+    __device__ static void mma(float* c, const uint32_t* a, const uint32_t* b) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+};
+
+__device__ __forceinline__ float silu_f(float v) { return v * rcp_approx(1.f + ex2(-v * kLog2e)); }
+
+// ---- staging of the activation tile [kc][64 px] (+ optional LN / gate prologue) --------------------------
+template <typename in_t, typename st_t>
+__device__ __forceinline__ void stage_x(st_t* __restrict__ sX, int XP, const PixlinParams& p, int b, int p0, int k0, int kc,
+                                        int kpad) {
+    constexpr int V = Vec<in_t>::N;
+    const in_t* __restrict__ xb = reinterpret_cast<const in_t*>(p.x) + (int64_t)b * p.x_bs;
+    const int groups = PL_PT / V;
+    for (int it = threadIdx.x; it < kpad * groups; it += PL_THREADS) {
+        const int k = it / groups, pg = (it % groups) * V;
+        float f[V];
+        if (k < kc) {
+            load_vec<in_t>(xb + (int64_t)(k0 + k) * p.x_cs + p0 + pg, f, p.P - (p0 + pg), p.vec_ok);
+        } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) f[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) sX[k * XP + pg + i] = st_t(f[i]);
+    }
+}
+
+template <typename st_t>
+__device__ __forceinline__ void prologue(st_t* __restrict__ sX, int XP, const PixlinParams& p, int b, int K, float* sStat) {
+    if (p.ln_mode) {
+        __syncthreads();
+        // per-pixel statistics over the K channels (two-pass, fp32) -- 2 threads per pixel
+        const int px = threadIdx.x % PL_PT, half = threadIdx.x / PL_PT;
+        float s = 0.f;
+        for (int k = half; k < K; k += 2) s += float(sX[k * XP + px]);
+        sStat[half * PL_PT + px] = s;
+        __syncthreads();
+        const float mu = (sStat[px] + sStat[PL_PT + px]) / K;
+        __syncthreads();
+        float v = 0.f;
+        for (int k = half; k < K; k += 2) {
+            const float dlt = float(sX[k * XP + px]) - mu;
+            v += dlt * dlt;
+        }
+        sStat[half * PL_PT + px] = v;
+        __syncthreads();
+        const float rstd = rsqrtf((sStat[px] + sStat[PL_PT + px]) / K + 1e-5f);
+        __syncthreads();
+        sStat[px] = mu;
+        sStat[PL_PT + px] = rstd;
+        __syncthreads();
+        for (int it = threadIdx.x; it < K * PL_PT; it += PL_THREADS) {
+            const int k = it / PL_PT, q = it % PL_PT;
+            float xv = float(sX[k * XP + q]);
+            xv = p.ln_mode == 1 ? (xv - sStat[q]) * sStat[PL_PT + q] * p.ln_w[k] + p.ln_b[k] : xv * sStat[PL_PT + q] * p.ln_w[k];
+            sX[k * XP + q] = st_t(xv);
+        }
+    }
+    if (p.gate_mode) {
+        __syncthreads();
+        const float* __restrict__ g = p.gate + (int64_t)b * p.g_bs;
+        for (int it = threadIdx.x; it < K * PL_PT; it += PL_THREADS) {
+            const int k = it / PL_PT, q = it % PL_PT;
+            const float xv = float(sX[k * XP + q]);
+            sX[k * XP + q] = st_t(p.gate_mode == 1 ? fmaf(xv, g[k], xv) : xv + g[k]);
+        }
+    }
+}
+
+template <typename in_t, typename st_t>
+__device__ __forceinline__ void stage_w(st_t* __restrict__ sW, int WP, const PixlinParams& p, int m0, int k0, int kc, int kpad) {
+    constexpr int V = Vec<in_t>::N;
+    const in_t* __restrict__ w = reinterpret_cast<const in_t*>(p.w);
+    const int groups = kpad / V;  // kpad is a multiple of 16
+    const bool vec = p.w_vec;     // rows 16 B aligned and padded (w_ld % V == 0, w_ld >= kpad_all)
+    for (int it = threadIdx.x; it < PL_MT * groups; it += PL_THREADS) {
+        const int m = it / groups, k = (it % groups) * V;
+        float f[V];
+        if (m0 + m < p.M) {
+            load_vec<in_t>(w + (int64_t)(m0 + m) * p.w_ld + k0 + k, f, vec ? V : kc - k, vec);
+            if (!vec) {
+#pragma unroll
+                for (int i = 0; i < V; ++i) f[i] = (k + i < kc) ? f[i] : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) f[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) sW[m * WP + k + i] = st_t(f[i]);
+    }
+}
+
+// ---- epilogue from the fp32 smem tile: bias, SiLU range, residual, store ---------------------------------
+template <typename in_t, typename out_t>
+__device__ __forceinline__ void epilogue(const float* __restrict__ sOut, int OP, const PixlinParams& p, int b, int p0, int m0) {
+    constexpr int G = 8;  // pixels per item
+    const in_t* __restrict__ res = p.residual ? reinterpret_cast<const in_t*>(p.residual) + (int64_t)b * p.r_bs : nullptr;
+    out_t* __restrict__ ob = reinterpret_cast<out_t*>(p.out) + (int64_t)b * p.o_bs;
+    for (int it = threadIdx.x; it < PL_MT * (PL_PT / G); it += PL_THREADS) {
+        const int m = it / (PL_PT / G), q = (it % (PL_PT / G)) * G;
+        const int mg = m0 + m;
+        if (mg >= p.M) continue;
+        const int valid = p.P - (p0 + q);
+        if (valid <= 0) continue;
+        float v[G];
+        const float bs = p.bias ? p.bias[mg] : 0.f;
+        const bool act = mg >= p.act_from && mg < p.act_to;
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            float t = sOut[m * OP + q + i] + bs;
+            v[i] = act ? silu_f(t) : t;
+        }
+        if (res) {
+            float r[G];
+            constexpr int VI = Vec<in_t>::N;
+#pragma unroll
+            for (int j = 0; j < G / VI; ++j) load_vec<in_t>(res + (int64_t)mg * p.r_cs + p0 + q + j * VI, r + j * VI, valid - j * VI, p.vec_ok);
+#pragma unroll
+            for (int i = 0; i < G; ++i) v[i] += r[i];
+        }
+        constexpr int VO = Vec<out_t>::N;
+#pragma unroll
+        for (int j = 0; j < G / VO; ++j) store_vec<out_t>(ob + (int64_t)mg * p.o_cs + p0 + q + j * VO, v + j * VO, valid - j * VO, p.vec_ok);
+    }
+}
+
+// ---- tensor-core kernel (bf16 / fp16 I/O) ----------------------------------------------------------------
+template <typename in_t, typename out_t>
+__global__ void __launch_bounds__(PL_THREADS) pixlin_mma_kernel(const PixlinParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int kpad_all = (p.K + 15) / 16 * 16;
+    const int KC = min(kpad_all, PL_KC);
+    const int XP = PL_PT + 8, WP = KC + 8, OP = PL_PT + 4;
+    in_t* sX = reinterpret_cast<in_t*>(smem_raw);                  // [KC][XP]
+    in_t* sW = sX + KC * XP;                                       // [MT][WP]
+    float* sOut = reinterpret_cast<float*>(sW + PL_MT * WP);       // [MT][OP]
+    float* sStat = sOut + PL_MT * OP;                              // [2][PT]
+    const int b = blockIdx.z, p0 = blockIdx.x * PL_PT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkc = (kpad_all + KC - 1) / KC;
+    const bool resident = nkc == 1;
+
+    if (resident) {
+        stage_x<in_t, in_t>(sX, XP, p, b, p0, 0, p.K, KC);
+        prologue<in_t>(sX, XP, p, b, p.K, sStat);
+    }
+    for (int m0 = blockIdx.y * PL_MT; m0 < p.M; m0 += gridDim.y * PL_MT) {
+        float acc[4][2][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+        for (int kc_i = 0; kc_i < nkc; ++kc_i) {
+            const int k0 = kc_i * KC, kc = min(p.K - k0, KC), kpad = (kc + 15) / 16 * 16;
+            __syncthreads();  // previous tile consumers done
+            if (!resident) stage_x<in_t, in_t>(sX, XP, p, b, p0, k0, kc, kpad);
+            stage_w<in_t, in_t>(sW, WP, p, m0, k0, kc, kpad);
+            __syncthreads();
+            for (int kk = 0; kk < kpad; kk += 16) {
+                uint32_t bf[4];
+                {
+                    const in_t* addr = sX + (kk + (lane & 15)) * XP + warp * 16 + ((lane >> 4) << 3);
+                    const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(addr));
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(bf[0]), "=r"(bf[1]), "=r"(bf[2]), "=r"(bf[3]) : "r"(sa));
+                }
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+                    uint32_t af[4];
+                    const in_t* addr = sW + (mi * 16 + (lane & 15)) * WP + kk + ((lane >> 4) << 3);
+                    const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(addr));
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(af[0]), "=r"(af[1]), "=r"(af[2]), "=r"(af[3]) : "r"(sa));
+                    MmaType<in_t>::mma(acc[mi][0], af, bf);
+                    MmaType<in_t>::mma(acc[mi][1], af, bf + 2);
+                }
+            }
+        }
+        // accumulators -> fp32 smem tile
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) {
+                const int row = mi * 16 + (lane >> 2), col = warp * 16 + ni * 8 + 2 * (lane & 3);
+                *reinterpret_cast<float2*>(&sOut[row * OP + col]) = make_float2(acc[mi][ni][0], acc[mi][ni][1]);
+                *reinterpret_cast<float2*>(&sOut[(row + 8) * OP + col]) = make_float2(acc[mi][ni][2], acc[mi][ni][3]);
+            }
+        __syncthreads();
+        epilogue<in_t, out_t>(sOut, OP, p, b, p0, m0);
+    }
+}
+
+// ---- fp32 kernel (FFMA) ----------------------------------------------------------------------------------
+template <typename out_t>
+__global__ void __launch_bounds__(PL_THREADS) pixlin_f32_kernel(const PixlinParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int kpad_all = (p.K + 15) / 16 * 16;
+    const int KC = min(kpad_all, PL_KC / 2);
+    const int XP = PL_PT + 4, WP = KC + 1, OP = PL_PT + 4;
+    float* sX = reinterpret_cast<float*>(smem_raw);   // [KC][XP]
+    float* sW = sX + KC * XP;                         // [MT][WP]
+    float* sOut = sW + PL_MT * WP;                    // [MT][OP]
+    float* sStat = sOut + PL_MT * OP;
+    const int b = blockIdx.z, p0 = blockIdx.x * PL_PT;
+    const int tm = threadIdx.x / 8, tp = threadIdx.x % 8;  // 16 x 8 thread grid: 4 rows x 8 pixels each
+    const int nkc = (kpad_all + KC - 1) / KC;
+    const bool resident = nkc == 1;
+    if (resident) {
+        stage_x<float, float>(sX, XP, p, b, p0, 0, p.K, KC);
+        prologue<float>(sX, XP, p, b, p.K, sStat);
+    }
+    for (int m0 = blockIdx.y * PL_MT; m0 < p.M; m0 += gridDim.y * PL_MT) {
+        float acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int kc_i = 0; kc_i < nkc; ++kc_i) {
+            const int k0 = kc_i * KC, kc = min(p.K - k0, KC), kpad = (kc + 15) / 16 * 16;
+            __syncthreads();
+            if (!resident) stage_x<float, float>(sX, XP, p, b, p0, k0, kc, kpad);
+            stage_w<float, float>(sW, WP, p, m0, k0, kc, kpad);
+            __syncthreads();
+            for (int k = 0; k < kc; ++k) {
+                const float4 x0 = *reinterpret_cast<const float4*>(&sX[k * XP + tp * 8]);
+                const float4 x1 = *reinterpret_cast<const float4*>(&sX[k * XP + tp * 8 + 4]);
+                const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float wv = sW[(tm * 4 + i) * WP + k];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(wv, xs[j], acc[i][j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sOut[(tm * 4 + i) * OP + tp * 8 + j] = acc[i][j];
+        __syncthreads();
+        epilogue<float, out_t>(sOut, OP, p, b, p0, m0);
+    }
+}
+
+static size_t pixlin_smem(int K, int elt) {
+    const int kpad = (K + 15) / 16 * 16;
+    if (elt == 2) {
+        const int KC = kpad < PL_KC ? kpad : PL_KC;
+        return (size_t)2 * (KC * (PL_PT + 8) + PL_MT * (KC + 8)) + 4 * (PL_MT * (PL_PT + 4) + 2 * PL_PT);
+    }
+    const int KC = kpad < PL_KC / 2 ? kpad : PL_KC / 2;
+    return (size_t)4 * (KC * (PL_PT + 4) + PL_MT * (KC + 1) + PL_MT * (PL_PT + 4) + 2 * PL_PT);
+}
+
+template <typename K>
+static int launch(K kern, const PixlinParams& p, size_t smem, cudaStream_t stream) {
+    if (smem > 48 * 1024) VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // split the output channels over blockIdx.y until the grid covers the 148 SMs a few times
+    const int ptiles = (p.P + PL_PT - 1) / PL_PT, mtiles = (p.M + PL_MT - 1) / PL_MT;
+    int msplit = 1;
+    while (msplit < mtiles && (long)ptiles * p.B * msplit < 148L * 3) ++msplit;
+    dim3 grid(ptiles, msplit, p.B);
+    kern<<<grid, PL_THREADS, smem, stream>>>(p);
+    VMB_CUDA(cudaGetLastError());
+    return VMB_OK;
+}
+
+int pixlin_launch(const PixlinParams& p, int dtype, int out_dtype, cudaStream_t stream) {
+    VMB_CHECK(p.ln_mode == 0 || p.K <= (dtype == VMB_F32 ? PL_KC / 2 : PL_KC), "pixlin: LayerNorm prologue needs K <= %d",
+              dtype == VMB_F32 ? PL_KC / 2 : PL_KC);
+    VMB_CHECK(p.gate_mode == 0 || p.K <= (dtype == VMB_F32 ? PL_KC / 2 : PL_KC), "pixlin: gate prologue needs resident K");
+    const size_t smem = pixlin_smem(p.K, dtype == VMB_F32 ? 4 : 2);
+    if (dtype == VMB_F32) {
+        VMB_CHECK(out_dtype == VMB_F32, "pixlin: fp32 input needs fp32 output");
+        return launch(pixlin_f32_kernel<float>, p, smem, stream);
+    }
+    if (dtype == VMB_BF16) {
+        if (out_dtype == VMB_F32) return launch(pixlin_mma_kernel<__nv_bfloat16, float>, p, smem, stream);
+        return launch(pixlin_mma_kernel<__nv_bfloat16, __nv_bfloat16>, p, smem, stream);
+    }
+    if (dtype == VMB_F16) {
+        if (out_dtype == VMB_F32) return launch(pixlin_mma_kernel<__half, float>, p, smem, stream);
+        return launch(pixlin_mma_kernel<__half, __half>, p, smem, stream);
+    }
+    set_error("pixlin: unsupported dtype %d", dtype);
+    return VMB_ERR_INVALID;
+}
+
+}  // namespace vmb

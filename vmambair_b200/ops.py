@@ -141,3 +141,87 @@ def selective_scan_bwd(u, delta, A, B, C_, D, delta_bias, dout, ckpt, delta_soft
     with torch.cuda.device(u.device), _timed("scan_bwd", nbytes, u.device, 2):
         _lib.check(L.vmb_selective_scan_bwd(C.byref(a), _stream(u)), "selective_scan_bwd")
     return du, ddelta, dA, dB, dC, dD, dbias
+
+
+# ----------------------------------------------------------------------------- fused OSS-block stages
+def _run(name, args, t, tag, nbytes=0, kernels=1):
+    fn = getattr(_lib.lib(), name)
+    with torch.cuda.device(t.device), _timed(tag, nbytes, t.device, kernels):
+        _lib.check(fn(C.byref(args), _stream(t)), name)
+
+
+def pixlin(x, w, bias=None, residual=None, ln=None, gate=None, gate_mode=0, act=(0, 0), out_dtype=None, out=None):
+    """out[b,m,p] = epi(sum_k w[m,k] pro(x)[b,k,p]).  x: (B,K,P) view with stride(-1)==1; w: (M,>=K) x.dtype, rows may be
+    zero-padded to a multiple of 16 (pad_weight) for vector loads.
+    ln = (mode, weight_fp32, bias_fp32|None); gate: (B,K) fp32; residual: (B,M,P) view."""
+    B, K, P = x.shape
+    M = w.shape[0]
+    assert w.shape[1] >= K and w.dtype == x.dtype and w.stride(1) == 1 and x.stride(2) == 1
+    out_dtype = out_dtype or x.dtype
+    if out is None:
+        out = torch.empty((B, M, P), dtype=out_dtype, device=x.device)
+    ln_mode, ln_w, ln_b = ln if ln is not None else (0, None, None)
+    a = _lib.PixlinArgs(
+        _ptr(x), _ptr(w), _ptr(bias), _ptr(residual), _ptr(out), _ptr(ln_w), _ptr(ln_b), _ptr(gate),
+        ln_mode, gate_mode if gate is not None else 0, act[0], act[1], B, K, M, P,
+        x.stride(0), x.stride(1), residual.stride(0) if residual is not None else 0,
+        residual.stride(1) if residual is not None else 0, out.stride(0), out.stride(1),
+        gate.stride(0) if gate is not None else 0, w.stride(0), _DT[x.dtype], _DT[out_dtype])
+    _run("vmb_pixlin", a, x, "pixlin", 0)
+    return out
+
+
+def pad_weight(w: torch.Tensor) -> torch.Tensor:
+    """(M,K) -> (M, ceil16(K)) zero-padded copy: rows 16 B aligned for the vectorised weight staging."""
+    M, K = w.shape
+    kp = (K + 15) // 16 * 16
+    if kp == K:
+        return w.contiguous()
+    out = torch.zeros((M, kp), dtype=w.dtype, device=w.device)
+    out[:, :K] = w
+    return out
+
+
+def dwconv3x3(x, w9, bias, c_out, H, W, mode):
+    """x: (B, Cin, H*W) view; mode 0: SiLU(dw(x[:c_out])); mode 1: gelu(dw(x[:c_out])) * dw(x[c_out:2c_out])."""
+    B = x.shape[0]
+    out = torch.empty((B, c_out, H * W), dtype=x.dtype, device=x.device)
+    a = _lib.DwconvArgs(_ptr(x), _ptr(w9), _ptr(bias), _ptr(out), B, c_out, H, W, mode,
+                        x.stride(0), x.stride(1), out.stride(0), out.stride(1), _DT[x.dtype])
+    _run("vmb_dwconv3x3", a, x, "dwconv")
+    return out
+
+
+def cross_scan(srcs, rows, H, W):
+    """srcs: 4 views (B, rows, L) sharing strides -> (B, 4, rows, L) in scan order."""
+    s0 = srcs[0]
+    B = s0.shape[0]
+    out = torch.empty((B, 4, rows, H * W), dtype=s0.dtype, device=s0.device)
+    arr = (C.c_void_p * 4)(*[t.data_ptr() for t in srcs])
+    for t in srcs:
+        assert t.stride() == s0.stride() and t.stride(2) == 1
+    a = _lib.CrossScanArgs(arr, _ptr(out), B, rows, H, W, s0.stride(0), s0.stride(1), out.stride(0), _DT[s0.dtype])
+    _run("vmb_cross_scan", a, s0, "cross_scan")
+    return out
+
+
+def merge_norm_gate(ys, z, ln_w, ln_b, C_, H, W):
+    """ys: (B,4,C,L) contiguous; z: (B,C,L) view -> (y2 (B,C,L), pooled sums (B,C) fp32)."""
+    B = ys.shape[0]
+    assert ys.is_contiguous() and z.stride(2) == 1
+    y2 = torch.empty((B, C_, H * W), dtype=ys.dtype, device=ys.device)
+    pooled = torch.zeros((B, C_), dtype=torch.float32, device=ys.device)
+    a = _lib.MergeArgs(_ptr(ys), _ptr(z), _ptr(ln_w), _ptr(ln_b), _ptr(y2), _ptr(pooled), B, C_, H, W,
+                       z.stride(0), z.stride(1), _DT[ys.dtype])
+    _run("vmb_merge_norm_gate", a, ys, "merge")
+    return y2, pooled
+
+
+def channel_branch(pooled, inv_count, prm, C_):
+    B = pooled.shape[0]
+    c = torch.empty((B, C_), dtype=torch.float32, device=pooled.device)
+    a = _lib.ChannelArgs(_ptr(pooled), inv_count, _ptr(prm["cin_w"]), _ptr(prm["cin_b"]), _ptr(prm["xc_proj"]),
+                         _ptr(prm["dtc_w"]), _ptr(prm["dtc_b"]), _ptr(prm["Ac_logs"]), _ptr(prm["Dsc"]), _ptr(prm["cout_w"]),
+                         _ptr(prm["cout_b"]), _ptr(prm["cn_w"]), _ptr(prm["cn_b"]), _ptr(c), B, C_, prm["dc"], prm["Rc"], prm["N"])
+    _run("vmb_channel_branch", a, pooled, "channel")
+    return c
