@@ -2,9 +2,10 @@
 // (reference: Mamba/kernels/selective_scan/csrc/selective_scan/cus/selective_scan_fwd_kernel.cuh:61-172).
 //
 // Design (B200-first, not a port of the CUB block-scan kernel):
-//   * one WARP (= one CTA of 32 threads) owns RB rows (channels d of one (batch, group)) and walks
-//     the sequence in warp-chunks of (32/RB) segments x T=16 positions;
-//     lane -> (row = lane % RB, segment = lane / RB).  No block-level barrier anywhere.
+//   * one WARP owns RB rows (channels d of one (batch, group)) and walks the sequence in chunks of
+//     (32/RB) segments x T=16 positions; lane -> (row = lane % RB, segment = lane / RB).  The WPC warps
+//     of a CTA own different rows of the SAME group and share one staged B/C tile; they only meet at
+//     the two barriers around tile staging, never inside the state loop.
 //   * B/C for the group are staged once per chunk in shared memory as fp32 and read by
 //     BROADCAST (all rows of a warp read the same (n,l) word), so smem bandwidth is 1/RB of a
 //     row-per-warp design and L2 traffic for B/C is 1/RB of the reference's row-per-CTA design.
@@ -21,28 +22,113 @@
 
 namespace vmb {
 
+// ---- cooperative (whole CTA) staging -------------------------------------------------------------
 template <typename in_t, int RB>
-__global__ void __launch_bounds__(32, 16) scan_fwd_kernel(const ScanFwdParams p) {
+struct FwdRaw {
+    static constexpr int V = Vec<in_t>::N;
+    static constexpr int CHUNK = FwdCfg<RB>::CHUNK;
+    static constexpr int PITCH = CHUNK + V;  // +16 B: conflict-free row-strided 128-bit reads
+    static constexpr int OPR = CHUNK / V;    // 16-byte ops per row (power of two)
+    static constexpr size_t bc_bytes = sizeof(in_t) * (size_t)32 * PITCH;
+    static constexpr size_t io_bytes = sizeof(in_t) * (size_t)2 * RB * PITCH;
+};
+
+// rows [0,16) = B states, [16,32) = C states of the first state tile, positions [c0, c0+CHUNK)
+template <typename in_t, int RB, int NT>
+__device__ __forceinline__ void prefetch_bc_cta(in_t* __restrict__ raw, const in_t* __restrict__ Bg, const in_t* __restrict__ Cg,
+                                                int64_t B_ns, int64_t C_ns, int N, int c0, int L, int tid) {
+    using R = FwdRaw<in_t, RB>;
+    const bool full = c0 + R::CHUNK <= L;
+#pragma unroll
+    for (int it = tid; it < 32 * R::OPR; it += NT) {
+        const int row = it / R::OPR, l = (it % R::OPR) * R::V;
+        const int n = row & 15;
+        const in_t* src = (row < 16 ? Bg + (int64_t)n * B_ns : Cg + (int64_t)n * C_ns) + c0 + l;
+        int nbytes = 16;
+        if (!full) nbytes = min(max((L - (c0 + l)) * (int)sizeof(in_t), 0), 16);
+        if (n >= N) nbytes = 0;
+        cp_async16(raw + row * R::PITCH + l, nbytes > 0 ? (const void*)src : (const void*)Bg, nbytes);
+    }
+}
+// the warp's own rows: [0,RB) = u, [RB,2RB) = delta
+template <typename in_t, int RB>
+__device__ __forceinline__ void prefetch_io_warp(in_t* __restrict__ raw, const in_t* __restrict__ ublk, const in_t* __restrict__ dblk,
+                                                 int64_t u_ds, int64_t dl_ds, int c0, int L, int lane) {
+    using R = FwdRaw<in_t, RB>;
+    const bool full = c0 + R::CHUNK <= L;
+#pragma unroll
+    for (int it = lane; it < 2 * RB * R::OPR; it += 32) {
+        const int row = it / R::OPR, l = (it % R::OPR) * R::V;
+        const in_t* src = (row < RB ? ublk + (int64_t)row * u_ds : dblk + (int64_t)(row - RB) * dl_ds) + c0 + l;
+        int nbytes = 16;
+        if (!full) nbytes = min(max((L - (c0 + l)) * (int)sizeof(in_t), 0), 16);
+        cp_async16(raw + row * R::PITCH + l, nbytes > 0 ? (const void*)src : (const void*)ublk, nbytes);
+    }
+}
+// raw B or C rows -> fp32 float4 layout used by the passes (whole CTA)
+template <typename in_t, int RB, int NT>
+__device__ __forceinline__ void convert_bc_cta(float4* __restrict__ dst, const in_t* __restrict__ rawX, int tid) {
+    using R = FwdRaw<in_t, RB>;
     using Cfg = FwdCfg<RB>;
-    using R = RawCfg<in_t, RB>;
-    constexpr int SEGW = Cfg::SEGW, CHUNK = Cfg::CHUNK, SEGQ = Cfg::SEGQ, SLOTS = Cfg::SLOTS;
+    constexpr int V = R::V, LG = R::CHUNK / V;
+#pragma unroll
+    for (int it = tid; it < 8 * LG; it += NT) {
+        const int np = it / LG, l = (it % LG) * V;
+        float f0[V], f1[V];
+        load_vec_smem<in_t>(rawX + (2 * np) * R::PITCH + l, f0);
+        load_vec_smem<in_t>(rawX + (2 * np + 1) * R::PITCH + l, f1);
+        float4* d = dst + np * Cfg::SLOTS + (l / T) * Cfg::SEGQ + (l % T) / 2;
+#pragma unroll
+        for (int i = 0; i < V / 2; ++i) d[i] = make_float4(f0[2 * i], f1[2 * i], f0[2 * i + 1], f1[2 * i + 1]);
+    }
+}
+// synchronous fallback (unaligned tensors, state tiles beyond the first), whole CTA
+template <typename in_t, int RB, int NT>
+__device__ __forceinline__ void stage_bc_cta(float4* __restrict__ dst, const in_t* __restrict__ src, int64_t n_stride, int n0,
+                                             int N, int c0, int L, bool vec_ok, int tid) {
+    using Cfg = FwdCfg<RB>;
     constexpr int V = Vec<in_t>::N;
+    constexpr int LG = Cfg::CHUNK / V;
+    for (int it = tid; it < 8 * LG; it += NT) {
+        const int np = it / LG, l = (it % LG) * V;
+        const int n = n0 + 2 * np;
+        float f0[V], f1[V];
+        const int valid = L - (c0 + l);
+#pragma unroll
+        for (int i = 0; i < V; ++i) f0[i] = f1[i] = 0.f;
+        if (n < N) load_vec<in_t>(src + (int64_t)n * n_stride + c0 + l, f0, valid, vec_ok);
+        if (n + 1 < N) load_vec<in_t>(src + (int64_t)(n + 1) * n_stride + c0 + l, f1, valid, vec_ok);
+        float4* d = dst + np * Cfg::SLOTS + (l / T) * Cfg::SEGQ + (l % T) / 2;
+#pragma unroll
+        for (int i = 0; i < V / 2; ++i) d[i] = make_float4(f0[2 * i], f1[2 * i], f0[2 * i + 1], f1[2 * i + 1]);
+    }
+}
+
+template <typename in_t, int RB, int WPC>
+__global__ void __launch_bounds__(32 * WPC, 16 / WPC) scan_fwd_kernel(const ScanFwdParams p) {
+    using Cfg = FwdCfg<RB>;
+    using R = FwdRaw<in_t, RB>;
+    constexpr int SEGW = Cfg::SEGW, CHUNK = Cfg::CHUNK, SEGQ = Cfg::SEGQ, SLOTS = Cfg::SLOTS;
+    constexpr int V = Vec<in_t>::N, NT = 32 * WPC;
 
     extern __shared__ float4 smem_f4[];
-    float4* sB = smem_f4;                                         // [8][SLOTS]
-    float4* sC = sB + 8 * SLOTS;                                  // [8][SLOTS]
-    in_t* raw = reinterpret_cast<in_t*>(sC + 8 * SLOTS);          // RawCfg rows
-    float* sCarry = reinterpret_cast<float*>(reinterpret_cast<char*>(raw) + R::bytes);  // [RB][npad]
-    float* sA = sCarry + RB * p.npad;                             // [RB][npad]  A * log2(e)
+    float4* sB = smem_f4;                                                  // [8][SLOTS]   CTA-shared
+    float4* sC = sB + 8 * SLOTS;                                           // [8][SLOTS]
+    in_t* rawBC = reinterpret_cast<in_t*>(sC + 8 * SLOTS);                 // [32][PITCH]
+    char* warp_base = reinterpret_cast<char*>(rawBC) + R::bc_bytes;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const size_t per_warp = R::io_bytes + sizeof(float) * 2 * RB * p.npad;
+    in_t* raw = reinterpret_cast<in_t*>(warp_base + warp * per_warp);      // [2RB][PITCH] this warp's u / delta rows
+    float* sCarry = reinterpret_cast<float*>(reinterpret_cast<char*>(raw) + R::io_bytes);  // [RB][npad]
+    float* sA = sCarry + RB * p.npad;                                      // [RB][npad]  A * log2(e)
 
-    const int lane = threadIdx.x;
     const int r = lane % RB, sl = lane / RB;
-    const int blocks_per_batch = p.dim / RB;
-    const int b = blockIdx.x / blocks_per_batch;
-    const int d0 = (blockIdx.x % blocks_per_batch) * RB, d = d0 + r;
-    const int g = d0 / p.rows_per_group;
+    const int ctas_per_batch = p.dim / (RB * WPC);
+    const int b = blockIdx.x / ctas_per_batch;
+    const int d0 = ((blockIdx.x % ctas_per_batch) * WPC + warp) * RB, d = d0 + r;
+    const int g = d0 / p.rows_per_group;  // same for every warp of the CTA (RB*WPC divides the group)
     const int N = p.N, L = p.L, npad = p.npad;
-    const bool async_ok = p.vec_ok;  // 16 B-aligned rows: asynchronous prefetch path
+    const bool async_ok = p.vec_ok;
 
     const in_t* __restrict__ Bg = reinterpret_cast<const in_t*>(p.Bm) + (int64_t)b * p.B_bs + (int64_t)g * p.B_gs;
     const in_t* __restrict__ Cg = reinterpret_cast<const in_t*>(p.Cm) + (int64_t)b * p.C_bs + (int64_t)g * p.C_gs;
@@ -52,9 +138,11 @@ __global__ void __launch_bounds__(32, 16) scan_fwd_kernel(const ScanFwdParams p)
     const in_t* __restrict__ drow = dblk + (int64_t)r * p.dl_ds;
     in_t* __restrict__ orow = reinterpret_cast<in_t*>(p.out) + (int64_t)b * p.o_bs + (int64_t)d * p.o_ds;
 
-    const in_t* io_base[2] = {ublk, dblk};
-    const int64_t io_ds[2] = {p.u_ds, p.dl_ds};
-    if (async_ok) prefetch_chunk<in_t, RB, 2>(raw, io_base, io_ds, Bg, Cg, p.B_ns, p.C_ns, N, 0, L, lane);
+    if (async_ok) {
+        prefetch_bc_cta<in_t, RB, NT>(rawBC, Bg, Cg, p.B_ns, p.C_ns, N, 0, L, tid);
+        prefetch_io_warp<in_t, RB>(raw, ublk, dblk, p.u_ds, p.dl_ds, 0, L, lane);
+        cp_async_commit();
+    }
     for (int i = lane; i < RB * npad; i += 32) {
         const int rr = i / npad, n = i % npad;
         sA[i] = n < N ? p.A[(int64_t)(d0 + rr) * N + n] * kLog2e : 0.f;
@@ -70,17 +158,20 @@ __global__ void __launch_bounds__(32, 16) scan_fwd_kernel(const ScanFwdParams p)
         float uv[T], dt[T];
         if (async_ok) {
             cp_async_wait_all();
-            __syncwarp();
-            convert_bc<in_t, RB, 2>(sB, raw + (2 * RB) * R::PITCH, lane);
-            convert_bc<in_t, RB, 2>(sC, raw + (2 * RB + 16) * R::PITCH, lane);
+            __syncthreads();  // every copy has landed; every warp is done with the previous B/C tile
+            convert_bc_cta<in_t, RB, NT>(sB, rawBC, tid);
+            convert_bc_cta<in_t, RB, NT>(sC, rawBC + 16 * R::PITCH, tid);
 #pragma unroll
             for (int v = 0; v < T / V; ++v) {
                 load_vec_smem<in_t>(raw + r * R::PITCH + sl * T + v * V, uv + v * V);
                 load_vec_smem<in_t>(raw + (RB + r) * R::PITCH + sl * T + v * V, dt + v * V);
             }
-            __syncwarp();  // raw buffer fully consumed -> refill it with the next chunk while we compute
-            if (c0 + CHUNK < L)
-                prefetch_chunk<in_t, RB, 2>(raw, io_base, io_ds, Bg, Cg, p.B_ns, p.C_ns, N, c0 + CHUNK, L, lane);
+            __syncthreads();  // fp32 tile complete, raw buffers free -> refill them while we compute
+            if (c0 + CHUNK < L) {
+                prefetch_bc_cta<in_t, RB, NT>(rawBC, Bg, Cg, p.B_ns, p.C_ns, N, c0 + CHUNK, L, tid);
+                prefetch_io_warp<in_t, RB>(raw, ublk, dblk, p.u_ds, p.dl_ds, c0 + CHUNK, L, lane);
+                cp_async_commit();
+            }
         } else {
 #pragma unroll
             for (int v = 0; v < T / V; ++v) {
@@ -104,11 +195,11 @@ __global__ void __launch_bounds__(32, 16) scan_fwd_kernel(const ScanFwdParams p)
 
         for (int nt = 0; nt < ntiles; ++nt) {
             if (!async_ok || nt > 0) {  // synchronous staging: unaligned tensors, or state tiles beyond the first
-                __syncwarp();
-                stage_bc<in_t, Cfg>(sB, Bg, p.B_ns, nt * 16, N, c0, L, p.vec_ok, lane);
-                stage_bc<in_t, Cfg>(sC, Cg, p.C_ns, nt * 16, N, c0, L, p.vec_ok, lane);
+                __syncthreads();
+                stage_bc_cta<in_t, RB, NT>(sB, Bg, p.B_ns, nt * 16, N, c0, L, p.vec_ok, tid);
+                stage_bc_cta<in_t, RB, NT>(sC, Cg, p.C_ns, nt * 16, N, c0, L, p.vec_ok, tid);
+                __syncthreads();
             }
-            __syncwarp();
 
 #pragma unroll 1
             for (int np = 0; np < 8; ++np) {
@@ -173,49 +264,61 @@ __global__ void __launch_bounds__(32, 16) scan_fwd_kernel(const ScanFwdParams p)
     }
 }
 
-template <typename in_t, int RB>
+template <typename in_t, int RB, int WPC>
 static int launch_cfg(const ScanFwdParams& p, cudaStream_t stream) {
     using Cfg = FwdCfg<RB>;
-    auto kern = scan_fwd_kernel<in_t, RB>;
-    const size_t smem = Cfg::smem_bytes(p.npad) + RawCfg<in_t, RB>::bytes;
+    using R = FwdRaw<in_t, RB>;
+    auto kern = scan_fwd_kernel<in_t, RB, WPC>;
+    const size_t smem = sizeof(float4) * 16 * Cfg::SLOTS + R::bc_bytes + WPC * (R::io_bytes + sizeof(float) * 2 * RB * p.npad);
     VMB_CHECK(smem <= 227 * 1024, "selective_scan_fwd: dstate=%d needs %zu B of shared memory", p.N, smem);
     if (smem > 48 * 1024) VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long blocks = (long)p.batch * (p.dim / RB);
-    kern<<<(unsigned)blocks, 32, smem, stream>>>(p);
+    const long blocks = (long)p.batch * (p.dim / (RB * WPC));
+    kern<<<(unsigned)blocks, 32 * WPC, smem, stream>>>(p);
     VMB_CUDA(cudaGetLastError());
     return VMB_OK;
 }
 
-// Rows per warp: must divide the rows of a group.  Larger RB = less smem/L2 traffic for B/C and
-// fewer shuffle steps; smaller RB = more warps (parallelism) and longer warp-chunks.  Aim for
-// >= ~12 warps per SM, fall back to the smallest admissible RB for small problems.
-static int pick_rb(const ScanFwdParams& p) {
+// (rows per warp RB, warps per CTA WPC): RB*WPC must divide the rows of a group.  Small RB = more warps and
+// longer chunks (more parallelism, more shuffle steps); the CTA shares one B/C tile, so WPC as large as fits.
+static void pick_cfg(const ScanFwdParams& p, int& rb, int& wpc) {
     const int rpg = p.rows_per_group;
-    if (const char* e = getenv("VMB_SCAN_RB")) {  // tuning/debug override
-        const int rb = atoi(e);
-        if (rb > 0 && rb <= 32 && (rb & (rb - 1)) == 0 && rpg % rb == 0) return rb;
-    }
     const long rows = (long)p.batch * p.dim;
-    // measured on B200 (C=96, L=4096): RB=8 wins once there are >= ~6 warps per SM, RB=4 below that;
-    // RB<4 only when the group has fewer rows (their warp-chunks need > 50 KB of smem per warp).
-    int rb = 1;
-    while (rb < 8 && rpg % (rb * 2) == 0) rb *= 2;
-    if (rb == 8 && rows / 8 < 148L * 6 && rpg % 4 == 0) rb = 4;
-    if (rb == 8 && rpg % 16 == 0 && rows / 16 >= 148L * 64) rb = 16;
-    // short sequences: do not use a warp-chunk much longer than L
+    int env_rb = 0, env_wpc = 0;
+    if (const char* e = getenv("VMB_SCAN_RB")) env_rb = atoi(e);
+    if (const char* e = getenv("VMB_SCAN_WPC")) env_wpc = atoi(e);
+    // measured on B200 (bf16, C=96, L=4096; tools/scan_sustained.py): rows=384 -> RB=1, rows=3072 -> RB=2,
+    // rows=12288 -> RB=4..8 (all within 2 %); i.e. aim for >= ~1500 warps, then grow RB for cheaper scans.
+    rb = rows < 1536 ? 1 : rows < 8192 ? 2 : rows < 32768 ? 4 : 8;
+    while (rb > 1 && rpg % rb) rb >>= 1;
+    // short sequences: a warp-chunk should not be much longer than L
     while (rb < 32 && rpg % (rb * 2) == 0 && (32 / rb) * T >= 2 * p.L) rb *= 2;
-    return rb;
+    if (env_rb > 0 && env_rb <= 32 && (env_rb & (env_rb - 1)) == 0 && rpg % env_rb == 0) rb = env_rb;
+    wpc = 4;
+    while (wpc > 1 && (rpg % (rb * wpc) != 0)) wpc >>= 1;
+    if (env_wpc > 0 && (env_wpc & (env_wpc - 1)) == 0 && rpg % (rb * env_wpc) == 0 && env_wpc <= 8) wpc = env_wpc;
+}
+
+template <typename in_t, int RB>
+static int launch_rb(const ScanFwdParams& p, int wpc, cudaStream_t stream) {
+    switch (wpc) {
+        case 8: return launch_cfg<in_t, RB, 8>(p, stream);
+        case 4: return launch_cfg<in_t, RB, 4>(p, stream);
+        case 2: return launch_cfg<in_t, RB, 2>(p, stream);
+        default: return launch_cfg<in_t, RB, 1>(p, stream);
+    }
 }
 
 template <typename in_t>
 static int launch_t(const ScanFwdParams& p, cudaStream_t stream) {
-    switch (pick_rb(p)) {
-        case 32: return launch_cfg<in_t, 32>(p, stream);
-        case 16: return launch_cfg<in_t, 16>(p, stream);
-        case 8: return launch_cfg<in_t, 8>(p, stream);
-        case 4: return launch_cfg<in_t, 4>(p, stream);
-        case 2: return launch_cfg<in_t, 2>(p, stream);
-        default: return launch_cfg<in_t, 1>(p, stream);
+    int rb, wpc;
+    pick_cfg(p, rb, wpc);
+    switch (rb) {
+        case 32: return launch_rb<in_t, 32>(p, wpc, stream);
+        case 16: return launch_rb<in_t, 16>(p, wpc, stream);
+        case 8: return launch_rb<in_t, 8>(p, wpc, stream);
+        case 4: return launch_rb<in_t, 4>(p, wpc, stream);
+        case 2: return launch_rb<in_t, 2>(p, wpc, stream);
+        default: return launch_rb<in_t, 1>(p, wpc, stream);
     }
 }
 
