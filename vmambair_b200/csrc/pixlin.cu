@@ -160,70 +160,227 @@ __device__ __forceinline__ void epilogue(const float* __restrict__ sOut, int OP,
 }
 
 // ---- tensor-core kernel (bf16 / fp16 I/O) ----------------------------------------------------------------
-template <typename in_t, typename out_t>
-__global__ void __launch_bounds__(PL_THREADS) pixlin_mma_kernel(const PixlinParams p) {
+// 256 threads = 8 warps as 2 (M halves of 32) x 4 (pixel quarters of PT/4); the K x PT activation tile stays in
+// smem for all output-channel tiles; weight tiles (64 x K) arrive by cp.async, double-buffered, one barrier per tile;
+// each warp drains its accumulators through a private smem patch (no CTA barrier) into 64 B-contiguous row stores.
+constexpr int PL2_THREADS = 256;
+constexpr int PL2_KC = 384;  // resident K (LayerNorm prologue needs the whole K); larger K streams in chunks
+
+__device__ __forceinline__ void cp_async16_pl(void* smem_dst, const void* gsrc, int src_bytes) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+template <typename in_t, int PT>
+__device__ __forceinline__ void stage_x2(in_t* __restrict__ sX, int XP, const PixlinParams& p, int b, int p0, int k0, int kc,
+                                         int kpad) {
+    constexpr int V = Vec<in_t>::N;
+    const in_t* __restrict__ xb = reinterpret_cast<const in_t*>(p.x) + (int64_t)b * p.x_bs;
+    constexpr int groups = PT / V;
+    if (p.vec_ok) {  // asynchronous 16 B copies: every thread keeps all of its copies in flight (memory-level parallelism)
+        for (int it = threadIdx.x; it < kpad * groups; it += PL2_THREADS) {
+            const int k = it / groups, pg = (it % groups) * V;
+            const bool ok = k < kc && p0 + pg < p.P;
+            cp_async16_pl(sX + k * XP + pg, ok ? (const void*)(xb + (int64_t)(k0 + k) * p.x_cs + p0 + pg) : (const void*)xb,
+                          ok ? 16 : 0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        return;
+    }
+    for (int it = threadIdx.x; it < kpad * groups; it += PL2_THREADS) {
+        const int k = it / groups, pg = (it % groups) * V;
+        in_t tmp[V];
+        const int valid = p.P - (p0 + pg);
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+            tmp[i] = (k < kc && i < valid) ? xb[(int64_t)(k0 + k) * p.x_cs + p0 + pg + i] : from_f32<in_t>(0.f);
+        *reinterpret_cast<uint4*>(sX + k * XP + pg) = *reinterpret_cast<uint4*>(tmp);
+    }
+}
+
+template <typename in_t, int PT>
+__device__ __forceinline__ void prologue2(in_t* __restrict__ sX, int XP, const PixlinParams& p, int b, int K, float* sStat) {
+    // 256 threads: PT pixels x (256/PT) K-slices
+    constexpr int SL = PL2_THREADS / PT;
+    if (p.ln_mode) {
+        __syncthreads();
+        const int px = threadIdx.x % PT, sl = threadIdx.x / PT;
+        float s = 0.f;
+        for (int k = sl; k < K; k += SL) s += to_f32<in_t>(sX[k * XP + px]);
+        sStat[sl * PT + px] = s;
+        __syncthreads();
+        float mu = 0.f;
+#pragma unroll
+        for (int i = 0; i < SL; ++i) mu += sStat[i * PT + px];
+        mu /= K;
+        __syncthreads();
+        float v = 0.f;
+        for (int k = sl; k < K; k += SL) {
+            const float dlt = to_f32<in_t>(sX[k * XP + px]) - mu;
+            v += dlt * dlt;
+        }
+        sStat[sl * PT + px] = v;
+        __syncthreads();
+        float var = 0.f;
+#pragma unroll
+        for (int i = 0; i < SL; ++i) var += sStat[i * PT + px];
+        const float rstd = rsqrtf(var / K + 1e-5f);
+        for (int k = sl; k < K; k += SL) {
+            float xv = to_f32<in_t>(sX[k * XP + px]);
+            xv = p.ln_mode == 1 ? (xv - mu) * rstd * p.ln_w[k] + p.ln_b[k] : xv * rstd * p.ln_w[k];
+            sX[k * XP + px] = from_f32<in_t>(xv);
+        }
+    }
+    if (p.gate_mode) {
+        __syncthreads();
+        const float* __restrict__ g = p.gate + (int64_t)b * p.g_bs;
+        for (int it = threadIdx.x; it < K * PT; it += PL2_THREADS) {
+            const int k = it / PT, q = it % PT;
+            const float xv = to_f32<in_t>(sX[k * XP + q]);
+            sX[k * XP + q] = from_f32<in_t>(p.gate_mode == 1 ? fmaf(xv, g[k], xv) : xv + g[k]);
+        }
+    }
+}
+
+// weight tile [64][kpad] of output channels [m0, m0+64), K range [k0, k0+kc): cp.async when rows are padded/aligned
+template <typename in_t>
+__device__ __forceinline__ void stage_w2(in_t* __restrict__ sW, int WP, const PixlinParams& p, int m0, int k0, int kc, int kpad) {
+    constexpr int V = Vec<in_t>::N;
+    const in_t* __restrict__ w = reinterpret_cast<const in_t*>(p.w);
+    const int groups = kpad / V;
+    for (int it = threadIdx.x; it < PL_MT * groups; it += PL2_THREADS) {
+        const int m = it / groups, k = (it % groups) * V;
+        in_t* dst = sW + m * WP + k;
+        if (p.w_vec) {
+            const bool ok = m0 + m < p.M;
+            cp_async16_pl(dst, ok ? (const void*)(w + (int64_t)(m0 + m) * p.w_ld + k0 + k) : (const void*)w, ok ? 16 : 0);
+        } else {
+            in_t tmp[V];
+#pragma unroll
+            for (int i = 0; i < V; ++i)
+                tmp[i] = (m0 + m < p.M && k + i < kc) ? w[(int64_t)(m0 + m) * p.w_ld + k0 + k + i] : from_f32<in_t>(0.f);
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(tmp);
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <typename in_t, typename out_t, int PT>
+__global__ void __launch_bounds__(PL2_THREADS) pixlin_mma_kernel(const PixlinParams p) {
+    constexpr int WN = PT / 4;       // pixels per warp
+    constexpr int NT8 = WN / 8;      // n8 tiles per warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int kpad_all = (p.K + 15) / 16 * 16;
-    const int KC = min(kpad_all, PL_KC);
-    const int XP = PL_PT + 8, WP = KC + 8, OP = PL_PT + 4;
-    in_t* sX = reinterpret_cast<in_t*>(smem_raw);                  // [KC][XP]
-    in_t* sW = sX + KC * XP;                                       // [MT][WP]
-    float* sOut = reinterpret_cast<float*>(sW + PL_MT * WP);       // [MT][OP]
-    float* sStat = sOut + PL_MT * OP;                              // [2][PT]
-    const int b = blockIdx.z, p0 = blockIdx.x * PL_PT;
+    const int KC = min(kpad_all, PL2_KC);
+    const int XP = PT + 8, WP = KC + 8;
+    constexpr int OP = WN + 4;
+    in_t* sX = reinterpret_cast<in_t*>(smem_raw);                    // [KC][XP]
+    in_t* sW0 = sX + KC * XP;                                        // [2][64][WP]
+    float* sOut = reinterpret_cast<float*>(sW0 + 2 * PL_MT * WP);    // [8 warps][32][OP]
+    float* sStat = sOut + 8 * 32 * OP;                               // [256]
+    const int b = blockIdx.z, p0 = blockIdx.x * PT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp >> 2, wn = warp & 3;                         // 2 x 4 warp grid
     const int nkc = (kpad_all + KC - 1) / KC;
     const bool resident = nkc == 1;
+    const int mtiles = (p.M + PL_MT - 1) / PL_MT;
+    const int my_tiles = (mtiles - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int steps = my_tiles * nkc;  // (m-tile, k-chunk) steps of this CTA
 
+    auto step_m0 = [&](int s) { return ((int)blockIdx.y + (s / nkc) * (int)gridDim.y) * PL_MT; };
+    auto step_k0 = [&](int s) { return (s % nkc) * KC; };
+    if (steps > 0) stage_w2<in_t>(sW0, WP, p, step_m0(0), step_k0(0), min(p.K - step_k0(0), KC), min(kpad_all - step_k0(0), KC));
     if (resident) {
-        stage_x<in_t, in_t>(sX, XP, p, b, p0, 0, p.K, KC);
-        prologue<in_t>(sX, XP, p, b, p.K, sStat);
+        stage_x2<in_t, PT>(sX, XP, p, b, p0, 0, p.K, KC);
+        prologue2<in_t, PT>(sX, XP, p, b, p.K, sStat);
     }
-    for (int m0 = blockIdx.y * PL_MT; m0 < p.M; m0 += gridDim.y * PL_MT) {
-        float acc[4][2][4];
+    float acc[2][NT8][4];
+    float* myOut = sOut + warp * 32 * OP;
+    const in_t* __restrict__ res = p.residual ? reinterpret_cast<const in_t*>(p.residual) + (int64_t)b * p.r_bs : nullptr;
+    out_t* __restrict__ ob = reinterpret_cast<out_t*>(p.out) + (int64_t)b * p.o_bs;
+
+    for (int s = 0; s < steps; ++s) {
+        const int m0 = step_m0(s), k0 = step_k0(s);
+        const int kpad = min(kpad_all - k0, KC);
+        in_t* sW = sW0 + (s & 1) * PL_MT * WP;
+        if (s % nkc == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+                for (int j = 0; j < NT8; ++j)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
-        for (int kc_i = 0; kc_i < nkc; ++kc_i) {
-            const int k0 = kc_i * KC, kc = min(p.K - k0, KC), kpad = (kc + 15) / 16 * 16;
-            __syncthreads();  // previous tile consumers done
-            if (!resident) stage_x<in_t, in_t>(sX, XP, p, b, p0, k0, kc, kpad);
-            stage_w<in_t, in_t>(sW, WP, p, m0, k0, kc, kpad);
-            __syncthreads();
-            for (int kk = 0; kk < kpad; kk += 16) {
-                uint32_t bf[4];
-                {
-                    const in_t* addr = sX + (kk + (lane & 15)) * XP + warp * 16 + ((lane >> 4) << 3);
-                    const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(addr));
-                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                                 : "=r"(bf[0]), "=r"(bf[1]), "=r"(bf[2]), "=r"(bf[3]) : "r"(sa));
-                }
-#pragma unroll
-                for (int mi = 0; mi < 4; ++mi) {
-                    uint32_t af[4];
-                    const in_t* addr = sW + (mi * 16 + (lane & 15)) * WP + kk + ((lane >> 4) << 3);
-                    const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(addr));
-                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                                 : "=r"(af[0]), "=r"(af[1]), "=r"(af[2]), "=r"(af[3]) : "r"(sa));
-                    MmaType<in_t>::mma(acc[mi][0], af, bf);
-                    MmaType<in_t>::mma(acc[mi][1], af, bf + 2);
-                }
-            }
+                    for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
         }
-        // accumulators -> fp32 smem tile
+        if (!resident) {
+            __syncthreads();  // previous chunk's X fully consumed
+            stage_x2<in_t, PT>(sX, XP, p, b, p0, k0, min(p.K - k0, KC), kpad);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();  // W[s] (and X) visible to all; everyone is done reading the other W buffer
+        if (s + 1 < steps)
+            stage_w2<in_t>(sW0 + ((s + 1) & 1) * PL_MT * WP, WP, p, step_m0(s + 1), step_k0(s + 1),
+                           min(p.K - step_k0(s + 1), KC), min(kpad_all - step_k0(s + 1), KC));
+        for (int kk = 0; kk < kpad; kk += 16) {
+            uint32_t af[2][4], bf[NT8][2];
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < 2; ++ni) {
-                const int row = mi * 16 + (lane >> 2), col = warp * 16 + ni * 8 + 2 * (lane & 3);
-                *reinterpret_cast<float2*>(&sOut[row * OP + col]) = make_float2(acc[mi][ni][0], acc[mi][ni][1]);
-                *reinterpret_cast<float2*>(&sOut[(row + 8) * OP + col]) = make_float2(acc[mi][ni][2], acc[mi][ni][3]);
+            for (int mi = 0; mi < 2; ++mi) {
+                const in_t* addr = sW + (wm * 32 + mi * 16 + (lane & 15)) * WP + kk + ((lane >> 4) << 3);
+                const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(addr));
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(af[mi][0]), "=r"(af[mi][1]), "=r"(af[mi][2]), "=r"(af[mi][3]) : "r"(sa));
             }
-        __syncthreads();
-        epilogue<in_t, out_t>(sOut, OP, p, b, p0, m0);
+#pragma unroll
+            for (int nj = 0; nj < NT8; nj += 2) {
+                const in_t* addr = sX + (kk + (lane & 15)) * XP + wn * WN + nj * 8 + ((lane >> 4) << 3);
+                const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(addr));
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(bf[nj][0]), "=r"(bf[nj][1]), "=r"(bf[nj + 1][0]), "=r"(bf[nj + 1][1]) : "r"(sa));
+            }
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int nj = 0; nj < NT8; ++nj) MmaType<in_t>::mma(acc[mi][nj], af[mi], bf[nj]);
+        }
+        if (s % nkc != nkc - 1) continue;
+        // ---- epilogue of this output-channel tile: warp-private smem patch -> row-contiguous stores ----
+        __syncwarp();
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int nj = 0; nj < NT8; ++nj) {
+                const int row = mi * 16 + (lane >> 2), col = nj * 8 + 2 * (lane & 3);
+                *reinterpret_cast<float2*>(&myOut[row * OP + col]) = make_float2(acc[mi][nj][0], acc[mi][nj][1]);
+                *reinterpret_cast<float2*>(&myOut[(row + 8) * OP + col]) = make_float2(acc[mi][nj][2], acc[mi][nj][3]);
+            }
+        __syncwarp();
+        constexpr int G = 8, GPR = WN / G;  // 8-pixel groups per row
+        for (int it = lane; it < 32 * GPR; it += 32) {
+            const int row = it / GPR, q = (it % GPR) * G;
+            const int mg = m0 + wm * 32 + row;
+            const int pg = p0 + wn * WN + q;
+            const int valid = p.P - pg;
+            if (mg >= p.M || valid <= 0) continue;
+            float v[G];
+            const float bs = p.bias ? p.bias[mg] : 0.f;
+            const bool act = mg >= p.act_from && mg < p.act_to;
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const float t = myOut[row * OP + q + i] + bs;
+                v[i] = act ? silu_f(t) : t;
+            }
+            if (res) {
+                float rr[G];
+                constexpr int VI = Vec<in_t>::N;
+#pragma unroll
+                for (int j = 0; j < G / VI; ++j) load_vec<in_t>(res + (int64_t)mg * p.r_cs + pg + j * VI, rr + j * VI, valid - j * VI, p.vec_ok);
+#pragma unroll
+                for (int i = 0; i < G; ++i) v[i] += rr[i];
+            }
+            constexpr int VO = Vec<out_t>::N;
+#pragma unroll
+            for (int j = 0; j < G / VO; ++j) store_vec<out_t>(ob + (int64_t)mg * p.o_cs + pg + j * VO, v + j * VO, valid - j * VO, p.vec_ok);
+        }
     }
 }
 
@@ -279,14 +436,40 @@ __global__ void __launch_bounds__(PL_THREADS) pixlin_f32_kernel(const PixlinPara
     }
 }
 
-static size_t pixlin_smem(int K, int elt) {
+static size_t pixlin_smem(int K, int elt, int PT = 64) {
     const int kpad = (K + 15) / 16 * 16;
     if (elt == 2) {
-        const int KC = kpad < PL_KC ? kpad : PL_KC;
-        return (size_t)2 * (KC * (PL_PT + 8) + PL_MT * (KC + 8)) + 4 * (PL_MT * (PL_PT + 4) + 2 * PL_PT);
+        const int KC = kpad < PL2_KC ? kpad : PL2_KC;
+        return (size_t)2 * (KC * (PT + 8) + 2 * PL_MT * (KC + 8)) + 4 * (8 * 32 * (PT / 4 + 4) + 256);
     }
     const int KC = kpad < PL_KC / 2 ? kpad : PL_KC / 2;
     return (size_t)4 * (KC * (PL_PT + 4) + PL_MT * (KC + 1) + PL_MT * (PL_PT + 4) + 2 * PL_PT);
+}
+
+template <typename K>
+static int launch2(K kern, const PixlinParams& p, size_t smem, int PT, cudaStream_t stream) {
+    if (smem > 48 * 1024) VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ptiles = (p.P + PT - 1) / PT, mtiles = (p.M + PL_MT - 1) / PL_MT;
+    int msplit = 1;
+    while (msplit < mtiles && (long)ptiles * p.B * msplit < 148L * 2) ++msplit;
+    dim3 grid(ptiles, msplit, p.B);
+    kern<<<grid, PL2_THREADS, smem, stream>>>(p);
+    VMB_CUDA(cudaGetLastError());
+    return VMB_OK;
+}
+
+template <typename in_t>
+static int launch_mma(const PixlinParams& p, int out_dtype, cudaStream_t stream) {
+    // 128-pixel tiles when there are enough pixels to fill the GPU with them, else 64
+    const bool big = (long)((p.P + 127) / 128) * p.B >= 148 && pixlin_smem(p.K, 2, 128) <= 200 * 1024;
+    const int PT = big ? 128 : 64;
+    const size_t smem = pixlin_smem(p.K, 2, PT);
+    VMB_CHECK(smem <= 227 * 1024, "pixlin: K=%d needs %zu B of shared memory", p.K, smem);
+    if (out_dtype == VMB_F32)
+        return big ? launch2(pixlin_mma_kernel<in_t, float, 128>, p, smem, PT, stream)
+                   : launch2(pixlin_mma_kernel<in_t, float, 64>, p, smem, PT, stream);
+    return big ? launch2(pixlin_mma_kernel<in_t, in_t, 128>, p, smem, PT, stream)
+               : launch2(pixlin_mma_kernel<in_t, in_t, 64>, p, smem, PT, stream);
 }
 
 template <typename K>
@@ -303,22 +486,16 @@ static int launch(K kern, const PixlinParams& p, size_t smem, cudaStream_t strea
 }
 
 int pixlin_launch(const PixlinParams& p, int dtype, int out_dtype, cudaStream_t stream) {
-    VMB_CHECK(p.ln_mode == 0 || p.K <= (dtype == VMB_F32 ? PL_KC / 2 : PL_KC), "pixlin: LayerNorm prologue needs K <= %d",
-              dtype == VMB_F32 ? PL_KC / 2 : PL_KC);
-    VMB_CHECK(p.gate_mode == 0 || p.K <= (dtype == VMB_F32 ? PL_KC / 2 : PL_KC), "pixlin: gate prologue needs resident K");
+    VMB_CHECK(p.ln_mode == 0 || p.K <= (dtype == VMB_F32 ? PL_KC / 2 : PL2_KC), "pixlin: LayerNorm prologue needs K <= %d",
+              dtype == VMB_F32 ? PL_KC / 2 : PL2_KC);
+    VMB_CHECK(p.gate_mode == 0 || p.K <= (dtype == VMB_F32 ? PL_KC / 2 : PL2_KC), "pixlin: gate prologue needs resident K");
     const size_t smem = pixlin_smem(p.K, dtype == VMB_F32 ? 4 : 2);
     if (dtype == VMB_F32) {
         VMB_CHECK(out_dtype == VMB_F32, "pixlin: fp32 input needs fp32 output");
         return launch(pixlin_f32_kernel<float>, p, smem, stream);
     }
-    if (dtype == VMB_BF16) {
-        if (out_dtype == VMB_F32) return launch(pixlin_mma_kernel<__nv_bfloat16, float>, p, smem, stream);
-        return launch(pixlin_mma_kernel<__nv_bfloat16, __nv_bfloat16>, p, smem, stream);
-    }
-    if (dtype == VMB_F16) {
-        if (out_dtype == VMB_F32) return launch(pixlin_mma_kernel<__half, float>, p, smem, stream);
-        return launch(pixlin_mma_kernel<__half, __half>, p, smem, stream);
-    }
+    if (dtype == VMB_BF16) return launch_mma<__nv_bfloat16>(p, out_dtype, stream);
+    if (dtype == VMB_F16) return launch_mma<__half>(p, out_dtype, stream);
     set_error("pixlin: unsupported dtype %d", dtype);
     return VMB_ERR_INVALID;
 }
