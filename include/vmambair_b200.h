@@ -59,6 +59,22 @@ typedef struct {
 } vmb_scan_fwd_args;
 int vmb_selective_scan_fwd(const vmb_scan_fwd_args* a, void* stream);
 
+/* Direction-aware variant for the fused OSS path: group g (<= 4 groups, dim = ngroups * rows_per_group) reads its
+ * rows from its own tensors and, when rev[g] != 0, walks them backwards (sequence position l <-> memory index
+ * L-1-l for u, delta, B, C and out), so the four scan orders of cross_scan_2d
+ * (SRGAN/VmambaIR/archs/MambaSISR6_arch.py:401-404) need no flipped / gathered copies: directions 0,2 read the
+ * natural (H,W) tensors, directions 1,3 the (W,H)-transposed ones.  Strides are shared by the groups; u/delta/out
+ * rows are indexed inside the group.  Requires 16 B-aligned rows (seqlen % 8 == 0 for 16-bit I/O), dstate <= 16. */
+typedef struct {
+    const void* u[4]; const void* delta[4]; const void* Bm[4]; const void* Cm[4]; void* out[4]; int rev[4];
+    const float* A; const float* D; const float* delta_bias;   /* (dim, dstate), (dim), (dim): indexed by g*rows+r */
+    int batch, dim, seqlen, dstate, ngroups;
+    int64_t u_bs, u_ds, delta_bs, delta_ds, out_bs, out_ds, B_bs, B_ns, C_bs, C_ns;
+    int delta_softplus;
+    int dtype;
+} vmb_scan_grouped_args;
+int vmb_selective_scan_fwd_grouped(const vmb_scan_grouped_args* a, void* stream);
+
 /* selective_scan_cuda_core.bwd  (cus/selective_scan.cpp:241-349, kernel
  * cus/selective_scan_bwd_kernel.cuh:66-273).
  *   dout, du, ddelta : (batch, dim, seqlen) dtype `dt`
@@ -125,6 +141,10 @@ typedef struct {
 } vmb_cross_scan_args;
 int vmb_cross_scan(const vmb_cross_scan_args* a, void* stream);
 
+/* (B*C) planes of H x W -> W x H (the transposed copy of x that directions 1 and 3 scan). */
+typedef struct { const void* x; void* out; int planes, H, W; int dtype; } vmb_transpose_args;
+int vmb_transpose_hw(const vmb_transpose_args* a, void* stream);
+
 /* inverse orders + 4-way fp32 sum (:427-430 / CrossMerge) + out_norm (:433) + gate y*SiLU(z) (:493) +
  * per-(b,c) sums of the result for AdaptiveAvgPool2d (:441; `pooled` fp32 (B,C), caller zero-fills). */
 typedef struct {
@@ -132,6 +152,8 @@ typedef struct {
     int batch, C, H, W;
     int64_t z_bs, z_cs;
     int dtype;
+    int in_place_order; /* 0: ys[k] in scan order (k=2,3 reversed); 1: ys[0],ys[2] in natural (H,W) pixel order and
+                           ys[1],ys[3] in transposed (W,H) pixel order (outputs of vmb_selective_scan_fwd_grouped) */
 } vmb_merge_args;
 int vmb_merge_norm_gate(const vmb_merge_args* a, void* stream);
 

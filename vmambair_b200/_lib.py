@@ -71,7 +71,22 @@ class MergeArgs(C.Structure):
     _fields_ = [
         ("ys", vp), ("z", vp), ("ln_w", vp), ("ln_b", vp), ("y2", vp), ("pooled", vp),
         ("batch", C.c_int), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int),
-        ("z_bs", i64), ("z_cs", i64), ("dtype", C.c_int),
+        ("z_bs", i64), ("z_cs", i64), ("dtype", C.c_int), ("in_place_order", C.c_int),
+    ]
+
+
+class TransposeArgs(C.Structure):
+    _fields_ = [("x", vp), ("out", vp), ("planes", C.c_int), ("H", C.c_int), ("W", C.c_int), ("dtype", C.c_int)]
+
+
+class ScanGroupedArgs(C.Structure):
+    _fields_ = [
+        ("u", vp * 4), ("delta", vp * 4), ("Bm", vp * 4), ("Cm", vp * 4), ("out", vp * 4), ("rev", C.c_int * 4),
+        ("A", vp), ("D", vp), ("delta_bias", vp),
+        ("batch", C.c_int), ("dim", C.c_int), ("seqlen", C.c_int), ("dstate", C.c_int), ("ngroups", C.c_int),
+        ("u_bs", i64), ("u_ds", i64), ("delta_bs", i64), ("delta_ds", i64), ("out_bs", i64), ("out_ds", i64),
+        ("B_bs", i64), ("B_ns", i64), ("C_bs", i64), ("C_ns", i64),
+        ("delta_softplus", C.c_int), ("dtype", C.c_int),
     ]
 
 
@@ -96,6 +111,8 @@ SYMBOLS = {
     "vmb_dwconv3x3": (C.c_int, [C.POINTER(DwconvArgs), vp]),
     "vmb_cross_scan": (C.c_int, [C.POINTER(CrossScanArgs), vp]),
     "vmb_merge_norm_gate": (C.c_int, [C.POINTER(MergeArgs), vp]),
+    "vmb_transpose_hw": (C.c_int, [C.POINTER(TransposeArgs), vp]),
+    "vmb_selective_scan_fwd_grouped": (C.c_int, [C.POINTER(ScanGroupedArgs), vp]),
     "vmb_channel_branch": (C.c_int, [C.POINTER(ChannelArgs), vp]),
 }
 

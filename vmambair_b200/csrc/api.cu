@@ -145,7 +145,7 @@ extern "C" int vmb_merge_norm_gate(const vmb_merge_args* a, void* stream) {
     VMB_CHECK(a && a->ys && a->z && a->ln_w && a->ln_b && a->y2 && a->pooled, "merge: null pointer");
     VMB_CHECK(dt_ok(a->dtype), "merge: bad dtype");
     VMB_CHECK(a->batch > 0 && a->batch <= 65535, "merge: bad batch");
-    MergeParams p{a->ys, a->z, a->ln_w, a->ln_b, a->y2, a->pooled, a->batch, a->C, a->H, a->W, a->z_bs, a->z_cs};
+    MergeParams p{a->ys, a->z, a->ln_w, a->ln_b, a->y2, a->pooled, a->batch, a->C, a->H, a->W, a->z_bs, a->z_cs, a->in_place_order};
     return merge_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
 }
 
@@ -157,4 +157,41 @@ extern "C" int vmb_channel_branch(const vmb_channel_args* a, void* stream) {
     ChannelParams p{a->pooled, a->inv_count, a->cin_w, a->cin_b, a->xc_proj, a->dtc_w, a->dtc_b, a->Ac_logs, a->Dsc,
                     a->cout_w, a->cout_b, a->cn_w, a->cn_b, a->c_out, a->batch, a->C, a->dc, a->Rc, a->N};
     return channel_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vmb_transpose_hw(const vmb_transpose_args* a, void* stream) {
+    VMB_CHECK(a && a->x && a->out, "transpose: null pointer");
+    VMB_CHECK(dt_ok(a->dtype) && a->planes > 0 && a->H > 0 && a->W > 0, "transpose: bad arguments");
+    TransposeParams p{a->x, a->out, a->planes, a->H, a->W};
+    return transpose_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vmb_selective_scan_fwd_grouped(const vmb_scan_grouped_args* a, void* stream) {
+    VMB_CHECK(a != nullptr, "scan_fwd_grouped: null args");
+    VMB_CHECK(dt_ok(a->dtype), "scan_fwd_grouped: bad dtype");
+    VMB_CHECK(a->ngroups >= 1 && a->ngroups <= 4 && a->dim % a->ngroups == 0, "scan_fwd_grouped: 1..4 groups dividing dim");
+    VMB_CHECK(a->batch > 0 && a->batch <= 65535 && a->dim > 0 && a->seqlen > 0 && a->dstate > 0 && a->dstate <= 16,
+              "scan_fwd_grouped: bad sizes (dstate <= 16)");
+    VMB_CHECK(a->A != nullptr, "scan_fwd_grouped: A missing");
+    ScanFwdParams p{};
+    p.A = a->A; p.D = a->D; p.bias = a->delta_bias; p.ckpt = nullptr;
+    p.batch = a->batch; p.dim = a->dim; p.L = a->seqlen; p.N = a->dstate; p.G = a->ngroups;
+    p.npad = 16;
+    p.rows_per_group = a->dim / a->ngroups;
+    p.n_ckpt = 0;
+    p.u_bs = a->u_bs; p.u_ds = a->u_ds; p.dl_bs = a->delta_bs; p.dl_ds = a->delta_ds; p.o_bs = a->out_bs; p.o_ds = a->out_ds;
+    p.B_bs = a->B_bs; p.B_gs = 0; p.B_ns = a->B_ns; p.C_bs = a->C_bs; p.C_gs = 0; p.C_ns = a->C_ns;
+    p.softplus = a->delta_softplus;
+    const int v = 16 / elt_size(a->dtype);
+    auto mult = [v](int64_t s) { return s % v == 0; };
+    bool ok = mult(a->u_bs) && mult(a->u_ds) && mult(a->delta_bs) && mult(a->delta_ds) && mult(a->out_bs) && mult(a->out_ds) &&
+              mult(a->B_bs) && mult(a->B_ns) && mult(a->C_bs) && mult(a->C_ns) && a->seqlen % v == 0;
+    p.ndesc = a->ngroups;
+    for (int g = 0; g < a->ngroups; ++g) {
+        VMB_CHECK(a->u[g] && a->delta[g] && a->Bm[g] && a->Cm[g] && a->out[g], "scan_fwd_grouped: null tensor pointer (group %d)", g);
+        ok = ok && aligned16(a->u[g]) && aligned16(a->delta[g]) && aligned16(a->Bm[g]) && aligned16(a->Cm[g]) && aligned16(a->out[g]);
+        p.grp[g] = ScanGroupDesc{a->u[g], a->delta[g], a->Bm[g], a->Cm[g], a->out[g], a->rev[g]};
+    }
+    p.vec_ok = ok;
+    return scan_fwd_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
 }

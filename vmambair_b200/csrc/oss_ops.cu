@@ -176,6 +176,38 @@ int cross_scan_launch(const CrossScanParams& p, int dtype, cudaStream_t stream) 
     return VMB_OK;
 }
 
+// ------------------------------------------------------------------------------------------ plane transpose
+template <typename in_t>
+__global__ void __launch_bounds__(256) transpose_hw_kernel(const TransposeParams p) {
+    __shared__ float tile[32][33];
+    const int tiles_w = (p.W + 31) / 32;
+    const int h0 = (blockIdx.x / tiles_w) * 32, w0 = (blockIdx.x % tiles_w) * 32;
+    const int64_t plane = (int64_t)blockIdx.y * p.H * p.W;
+    const in_t* __restrict__ x = reinterpret_cast<const in_t*>(p.x) + plane;
+    in_t* __restrict__ o = reinterpret_cast<in_t*>(p.out) + plane;
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+#pragma unroll
+    for (int j = ty; j < 32; j += 8)
+        tile[j][tx] = (h0 + j < p.H && w0 + tx < p.W) ? to_f32<in_t>(x[(int64_t)(h0 + j) * p.W + w0 + tx]) : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int j = ty; j < 32; j += 8)
+        if (w0 + j < p.W && h0 + tx < p.H) o[(int64_t)(w0 + j) * p.H + h0 + tx] = from_f32<in_t>(tile[tx][j]);
+}
+
+int transpose_launch(const TransposeParams& p, int dtype, cudaStream_t stream) {
+    VMB_CHECK(p.planes <= 65535, "transpose: too many planes");
+    dim3 grid(((p.H + 31) / 32) * ((p.W + 31) / 32), p.planes);
+    switch (dtype) {
+        case VMB_F32: transpose_hw_kernel<float><<<grid, 256, 0, stream>>>(p); break;
+        case VMB_BF16: transpose_hw_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(p); break;
+        case VMB_F16: transpose_hw_kernel<__half><<<grid, 256, 0, stream>>>(p); break;
+        default: set_error("transpose: unsupported dtype %d", dtype); return VMB_ERR_INVALID;
+    }
+    VMB_CUDA(cudaGetLastError());
+    return VMB_OK;
+}
+
 // ------------------------------------------------------------------------------------------ merge + out_norm + gate + pool
 // CTA = (b, 8x8 pixel tile), all C channels.  Phase 1: sum the four directions in the reference's order,
 // (y0 + flip(y2)) + T(y1) + T(flip(y3)), fp32, into smem [C][64].  Phase 2: LayerNorm over C per pixel,
@@ -201,9 +233,9 @@ __global__ void __launch_bounds__(256) merge_norm_gate_kernel(const MergeParams 
         if (ok) {
             const in_t* __restrict__ yc = ys + (int64_t)c * L;
             const float y0 = to_f32<in_t>(yc[l_row]);
-            const float y2 = to_f32<in_t>(yc[(int64_t)2 * C * L + (L - 1 - l_row)]);
+            const float y2 = to_f32<in_t>(yc[(int64_t)2 * C * L + (p.in_place_order ? l_row : L - 1 - l_row)]);
             const float y1 = to_f32<in_t>(yc[(int64_t)1 * C * L + l_col]);
-            const float y3 = to_f32<in_t>(yc[(int64_t)3 * C * L + (L - 1 - l_col)]);
+            const float y3 = to_f32<in_t>(yc[(int64_t)3 * C * L + (p.in_place_order ? l_col : L - 1 - l_col)]);
             v = ((y0 + y2) + y1) + y3;
         }
         sY[c * 65 + q] = v;

@@ -26,6 +26,11 @@ struct MergeParams {
     const void* ys; const void* z; const float* ln_w; const float* ln_b; void* y2; float* pooled;
     int B, C, H, W;
     int64_t z_bs, z_cs;
+    int in_place_order;
+};
+struct TransposeParams {
+    const void* x; void* out;
+    int planes, H, W;
 };
 struct ChannelParams {
     const float* pooled; float inv_count;
@@ -38,6 +43,7 @@ int pixlin_launch(const PixlinParams& p, int dtype, int out_dtype, cudaStream_t 
 int dwconv_launch(const DwParams& p, int dtype, cudaStream_t stream);
 int cross_scan_launch(const CrossScanParams& p, int dtype, cudaStream_t stream);
 int merge_launch(const MergeParams& p, int dtype, cudaStream_t stream);
+int transpose_launch(const TransposeParams& p, int dtype, cudaStream_t stream);
 int channel_launch(const ChannelParams& p, cudaStream_t stream);
 }  // namespace vmb
 

@@ -34,18 +34,19 @@ struct FwdRaw {
 };
 
 // rows [0,16) = B states, [16,32) = C states of the first state tile, positions [c0, c0+CHUNK)
+// m0 = memory index of the chunk's first raw element: c0 (forward) or L - c0 - CHUNK (reversed walk, may be < 0)
 template <typename in_t, int RB, int NT>
 __device__ __forceinline__ void prefetch_bc_cta(in_t* __restrict__ raw, const in_t* __restrict__ Bg, const in_t* __restrict__ Cg,
-                                                int64_t B_ns, int64_t C_ns, int N, int c0, int L, int tid) {
+                                                int64_t B_ns, int64_t C_ns, int N, int m0, int L, int tid) {
     using R = FwdRaw<in_t, RB>;
-    const bool full = c0 + R::CHUNK <= L;
+    const bool full = m0 >= 0 && m0 + R::CHUNK <= L;
 #pragma unroll
     for (int it = tid; it < 32 * R::OPR; it += NT) {
         const int row = it / R::OPR, l = (it % R::OPR) * R::V;
         const int n = row & 15;
-        const in_t* src = (row < 16 ? Bg + (int64_t)n * B_ns : Cg + (int64_t)n * C_ns) + c0 + l;
+        const in_t* src = (row < 16 ? Bg + (int64_t)n * B_ns : Cg + (int64_t)n * C_ns) + m0 + l;
         int nbytes = 16;
-        if (!full) nbytes = min(max((L - (c0 + l)) * (int)sizeof(in_t), 0), 16);
+        if (!full) nbytes = (m0 + l < 0) ? 0 : min(max((L - (m0 + l)) * (int)sizeof(in_t), 0), 16);
         if (n >= N) nbytes = 0;
         cp_async16(raw + row * R::PITCH + l, nbytes > 0 ? (const void*)src : (const void*)Bg, nbytes);
     }
@@ -53,21 +54,21 @@ __device__ __forceinline__ void prefetch_bc_cta(in_t* __restrict__ raw, const in
 // the warp's own rows: [0,RB) = u, [RB,2RB) = delta
 template <typename in_t, int RB>
 __device__ __forceinline__ void prefetch_io_warp(in_t* __restrict__ raw, const in_t* __restrict__ ublk, const in_t* __restrict__ dblk,
-                                                 int64_t u_ds, int64_t dl_ds, int c0, int L, int lane) {
+                                                 int64_t u_ds, int64_t dl_ds, int m0, int L, int lane) {
     using R = FwdRaw<in_t, RB>;
-    const bool full = c0 + R::CHUNK <= L;
+    const bool full = m0 >= 0 && m0 + R::CHUNK <= L;
 #pragma unroll
     for (int it = lane; it < 2 * RB * R::OPR; it += 32) {
         const int row = it / R::OPR, l = (it % R::OPR) * R::V;
-        const in_t* src = (row < RB ? ublk + (int64_t)row * u_ds : dblk + (int64_t)(row - RB) * dl_ds) + c0 + l;
+        const in_t* src = (row < RB ? ublk + (int64_t)row * u_ds : dblk + (int64_t)(row - RB) * dl_ds) + m0 + l;
         int nbytes = 16;
-        if (!full) nbytes = min(max((L - (c0 + l)) * (int)sizeof(in_t), 0), 16);
+        if (!full) nbytes = (m0 + l < 0) ? 0 : min(max((L - (m0 + l)) * (int)sizeof(in_t), 0), 16);
         cp_async16(raw + row * R::PITCH + l, nbytes > 0 ? (const void*)src : (const void*)ublk, nbytes);
     }
 }
 // raw B or C rows -> fp32 float4 layout used by the passes (whole CTA)
 template <typename in_t, int RB, int NT>
-__device__ __forceinline__ void convert_bc_cta(float4* __restrict__ dst, const in_t* __restrict__ rawX, int tid) {
+__device__ __forceinline__ void convert_bc_cta(float4* __restrict__ dst, const in_t* __restrict__ rawX, int tid, bool rev) {
     using R = FwdRaw<in_t, RB>;
     using Cfg = FwdCfg<RB>;
     constexpr int V = R::V, LG = R::CHUNK / V;
@@ -77,9 +78,19 @@ __device__ __forceinline__ void convert_bc_cta(float4* __restrict__ dst, const i
         float f0[V], f1[V];
         load_vec_smem<in_t>(rawX + (2 * np) * R::PITCH + l, f0);
         load_vec_smem<in_t>(rawX + (2 * np + 1) * R::PITCH + l, f1);
-        float4* d = dst + np * Cfg::SLOTS + (l / T) * Cfg::SEGQ + (l % T) / 2;
+        if (!rev) {
+            float4* d = dst + np * Cfg::SLOTS + (l / T) * Cfg::SEGQ + (l % T) / 2;
 #pragma unroll
-        for (int i = 0; i < V / 2; ++i) d[i] = make_float4(f0[2 * i], f1[2 * i], f0[2 * i + 1], f1[2 * i + 1]);
+            for (int i = 0; i < V / 2; ++i) d[i] = make_float4(f0[2 * i], f1[2 * i], f0[2 * i + 1], f1[2 * i + 1]);
+        } else {
+            // raw index i <-> sequence position CHUNK-1-i: the V raw elements are V descending positions
+            const int s_hi = R::CHUNK - 1 - l;  // sequence position of raw element l (odd)
+#pragma unroll
+            for (int j = 0; j < V / 2; ++j) {
+                const int s = s_hi - 1 - 2 * j;  // even position of the pair (s, s+1) <- raw (l+2j+1, l+2j)
+                dst[np * Cfg::SLOTS + (s / T) * Cfg::SEGQ + (s % T) / 2] = make_float4(f0[2 * j + 1], f1[2 * j + 1], f0[2 * j], f1[2 * j]);
+            }
+        }
     }
 }
 // synchronous fallback (unaligned tensors, state tiles beyond the first), whole CTA
@@ -130,17 +141,32 @@ __global__ void __launch_bounds__(32 * WPC, 16 / WPC) scan_fwd_kernel(const Scan
     const int N = p.N, L = p.L, npad = p.npad;
     const bool async_ok = p.vec_ok;
 
-    const in_t* __restrict__ Bg = reinterpret_cast<const in_t*>(p.Bm) + (int64_t)b * p.B_bs + (int64_t)g * p.B_gs;
-    const in_t* __restrict__ Cg = reinterpret_cast<const in_t*>(p.Cm) + (int64_t)b * p.C_bs + (int64_t)g * p.C_gs;
-    const in_t* __restrict__ ublk = reinterpret_cast<const in_t*>(p.u) + (int64_t)b * p.u_bs + (int64_t)d0 * p.u_ds;
-    const in_t* __restrict__ dblk = reinterpret_cast<const in_t*>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)d0 * p.dl_ds;
+    const in_t *Bg, *Cg, *ublk, *dblk;
+    in_t* orow;
+    bool rev = false;
+    if (p.ndesc == 0) {
+        Bg = reinterpret_cast<const in_t*>(p.Bm) + (int64_t)b * p.B_bs + (int64_t)g * p.B_gs;
+        Cg = reinterpret_cast<const in_t*>(p.Cm) + (int64_t)b * p.C_bs + (int64_t)g * p.C_gs;
+        ublk = reinterpret_cast<const in_t*>(p.u) + (int64_t)b * p.u_bs + (int64_t)d0 * p.u_ds;
+        dblk = reinterpret_cast<const in_t*>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)d0 * p.dl_ds;
+        orow = reinterpret_cast<in_t*>(p.out) + (int64_t)b * p.o_bs + (int64_t)d * p.o_ds;
+    } else {  // per-group sources; rows are indexed inside the group
+        const ScanGroupDesc& gd = p.grp[g];
+        const int dg0 = d0 - g * p.rows_per_group;
+        Bg = reinterpret_cast<const in_t*>(gd.Bm) + (int64_t)b * p.B_bs;
+        Cg = reinterpret_cast<const in_t*>(gd.Cm) + (int64_t)b * p.C_bs;
+        ublk = reinterpret_cast<const in_t*>(gd.u) + (int64_t)b * p.u_bs + (int64_t)dg0 * p.u_ds;
+        dblk = reinterpret_cast<const in_t*>(gd.delta) + (int64_t)b * p.dl_bs + (int64_t)dg0 * p.dl_ds;
+        orow = reinterpret_cast<in_t*>(gd.out) + (int64_t)b * p.o_bs + (int64_t)(dg0 + r) * p.o_ds;
+        rev = gd.rev != 0;
+    }
     const in_t* __restrict__ urow = ublk + (int64_t)r * p.u_ds;
     const in_t* __restrict__ drow = dblk + (int64_t)r * p.dl_ds;
-    in_t* __restrict__ orow = reinterpret_cast<in_t*>(p.out) + (int64_t)b * p.o_bs + (int64_t)d * p.o_ds;
 
     if (async_ok) {
-        prefetch_bc_cta<in_t, RB, NT>(rawBC, Bg, Cg, p.B_ns, p.C_ns, N, 0, L, tid);
-        prefetch_io_warp<in_t, RB>(raw, ublk, dblk, p.u_ds, p.dl_ds, 0, L, lane);
+        const int m0 = rev ? L - CHUNK : 0;
+        prefetch_bc_cta<in_t, RB, NT>(rawBC, Bg, Cg, p.B_ns, p.C_ns, N, m0, L, tid);
+        prefetch_io_warp<in_t, RB>(raw, ublk, dblk, p.u_ds, p.dl_ds, m0, L, lane);
         cp_async_commit();
     }
     for (int i = lane; i < RB * npad; i += 32) {
@@ -159,17 +185,32 @@ __global__ void __launch_bounds__(32 * WPC, 16 / WPC) scan_fwd_kernel(const Scan
         if (async_ok) {
             cp_async_wait_all();
             __syncthreads();  // every copy has landed; every warp is done with the previous B/C tile
-            convert_bc_cta<in_t, RB, NT>(sB, rawBC, tid);
-            convert_bc_cta<in_t, RB, NT>(sC, rawBC + 16 * R::PITCH, tid);
+            convert_bc_cta<in_t, RB, NT>(sB, rawBC, tid, rev);
+            convert_bc_cta<in_t, RB, NT>(sC, rawBC + 16 * R::PITCH, tid, rev);
+            if (!rev) {
 #pragma unroll
-            for (int v = 0; v < T / V; ++v) {
-                load_vec_smem<in_t>(raw + r * R::PITCH + sl * T + v * V, uv + v * V);
-                load_vec_smem<in_t>(raw + (RB + r) * R::PITCH + sl * T + v * V, dt + v * V);
+                for (int v = 0; v < T / V; ++v) {
+                    load_vec_smem<in_t>(raw + r * R::PITCH + sl * T + v * V, uv + v * V);
+                    load_vec_smem<in_t>(raw + (RB + r) * R::PITCH + sl * T + v * V, dt + v * V);
+                }
+            } else {  // sequence positions sl*T+t live at raw index CHUNK-1-(sl*T+t)
+                float ur[T], dr[T];
+#pragma unroll
+                for (int v = 0; v < T / V; ++v) {
+                    load_vec_smem<in_t>(raw + r * R::PITCH + CHUNK - (sl + 1) * T + v * V, ur + v * V);
+                    load_vec_smem<in_t>(raw + (RB + r) * R::PITCH + CHUNK - (sl + 1) * T + v * V, dr + v * V);
+                }
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    uv[t] = ur[T - 1 - t];
+                    dt[t] = dr[T - 1 - t];
+                }
             }
             __syncthreads();  // fp32 tile complete, raw buffers free -> refill them while we compute
             if (c0 + CHUNK < L) {
-                prefetch_bc_cta<in_t, RB, NT>(rawBC, Bg, Cg, p.B_ns, p.C_ns, N, c0 + CHUNK, L, tid);
-                prefetch_io_warp<in_t, RB>(raw, ublk, dblk, p.u_ds, p.dl_ds, c0 + CHUNK, L, lane);
+                const int m0 = rev ? L - c0 - 2 * CHUNK : c0 + CHUNK;
+                prefetch_bc_cta<in_t, RB, NT>(rawBC, Bg, Cg, p.B_ns, p.C_ns, N, m0, L, tid);
+                prefetch_io_warp<in_t, RB>(raw, ublk, dblk, p.u_ds, p.dl_ds, m0, L, lane);
                 cp_async_commit();
             }
         } else {
@@ -259,8 +300,20 @@ __global__ void __launch_bounds__(32 * WPC, 16 / WPC) scan_fwd_kernel(const Scan
                 }
             }
         }
+        if (!rev) {
 #pragma unroll
-        for (int v = 0; v < T / V; ++v) store_vec<in_t>(orow + l0 + v * V, y + v * V, valid - v * V, p.vec_ok);
+            for (int v = 0; v < T / V; ++v) store_vec<in_t>(orow + l0 + v * V, y + v * V, valid - v * V, p.vec_ok);
+        } else if (valid == T) {  // sequence l0+t -> memory L-1-l0-t: one reversed contiguous block
+            float yr[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t) yr[t] = y[T - 1 - t];
+#pragma unroll
+            for (int v = 0; v < T / V; ++v) store_vec<in_t>(orow + (L - l0 - T) + v * V, yr + v * V, V, p.vec_ok);
+        } else {
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+                if (t < valid) orow[L - 1 - l0 - t] = from_f32<in_t>(y[t]);
+        }
     }
 }
 
@@ -324,6 +377,10 @@ static int launch_t(const ScanFwdParams& p, cudaStream_t stream) {
 
 int scan_fwd_launch(const ScanFwdParams& p, int dtype, cudaStream_t stream) {
     VMB_CHECK((long)p.batch * p.dim < (1L << 31), "selective_scan_fwd: batch*dim too large");
+    if (p.ndesc) {
+        VMB_CHECK(p.vec_ok && p.npad == 16, "grouped scan: needs 16 B-aligned rows (L %% 8 == 0) and dstate <= 16");
+        VMB_CHECK(p.ckpt == nullptr, "grouped scan: inference only (no checkpoints)");
+    }
     switch (dtype) {
         case VMB_F32: return launch_t<float>(p, stream);
         case VMB_BF16: return launch_t<__nv_bfloat16>(p, stream);

@@ -8,6 +8,14 @@ namespace vmb {
 constexpr int kScanT = 16;      // sequence positions per lane per chunk
 constexpr int kScanCkpt = 64;   // checkpoint interval (positions); see vmb_scan_ckpt_interval()
 
+// Per-group sources (direction-aware fused path): group g of the scan reads its rows from its own tensors and may
+// walk them backwards (rev: sequence position l <-> memory index L-1-l for u, delta, B, C and out).
+struct ScanGroupDesc {
+    const void *u, *delta, *Bm, *Cm;
+    void* out;
+    int rev;
+};
+
 struct ScanFwdParams {
     const void *u, *delta, *Bm, *Cm;
     const float *A, *D, *bias;
@@ -18,6 +26,8 @@ struct ScanFwdParams {
     int64_t B_bs, B_gs, B_ns, C_bs, C_gs, C_ns;
     int softplus;
     bool vec_ok;
+    int ndesc;              // 0: flat tensors (B0 operator); else = G <= 4 group descriptors (strides shared, per-group bases)
+    ScanGroupDesc grp[4];
 };
 
 struct ScanBwdParams {

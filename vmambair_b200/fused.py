@@ -10,6 +10,8 @@ No CPU path, no silent fallback: every stage goes through the C-ABI and raises o
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -44,6 +46,8 @@ def _prepare(block, dtype, device):
         w_in=w(a.in_conv.weight.view(2 * C, C)), b_in=_f32(a.in_conv.bias),
         dw=_f32(a.conv2d.weight.view(C, 9)), dw_b=_f32(a.conv2d.bias),
         w_big=w(big),
+        w_big02=w(torch.cat([big[0:C + 2 * N], big[2 * (C + 2 * N):3 * (C + 2 * N)]], 0)),
+        w_big13=w(torch.cat([big[(C + 2 * N):2 * (C + 2 * N)], big[3 * (C + 2 * N):]], 0)),
         A=(-torch.exp(a.A_logs.detach().float())).contiguous(), Ds=_f32(a.Ds), dt_bias=_f32(a.dt_projs_bias.view(-1)),
         on_w=_f32(a.out_norm.body.weight), on_b=_f32(a.out_norm.body.bias),
         ch=dict(cin_w=_f32(a.conv_cin.weight.view(-1)) if has_cio else None, cin_b=_f32(a.conv_cin.bias) if has_cio else None,
@@ -72,6 +76,17 @@ def block_forward(block, x: torch.Tensor) -> torch.Tensor:
     # norm1 + in_conv; SiLU on the z half
     xz = ops.pixlin(x3, c["w_in"], c["b_in"], ln=c["ln1"], act=(C, 2 * C))
     xc = ops.dwconv3x3(xz[:, :C], c["dw"], c["dw_b"], C, H, W, 0)
+    if L % 8 == 0 and os.environ.get("VMB_FUSED_SCAN", "grouped") == "grouped":
+        # direction-aware scan: directions 0/2 read x and the GEMM on x, 1/3 read the transposed copies; reversed
+        # directions walk the same memory backwards -- no gathered / flipped (B,4C,L) operands exist
+        xt = ops.transpose_hw(xc, H, W)
+        d02 = ops.pixlin(xc, c["w_big02"]).view(B, 2, C + 2 * N, L)
+        d13 = ops.pixlin(xt, c["w_big13"]).view(B, 2, C + 2 * N, L)
+        src = [(xc, d02[:, 0]), (xt, d13[:, 0]), (xc, d02[:, 1]), (xt, d13[:, 1])]
+        ys = ops.selective_scan_fwd_grouped([s[0] for s in src], [s[1][:, :C] for s in src], [s[1][:, C:C + N] for s in src],
+                                            [s[1][:, C + N:] for s in src], [0, 0, 1, 1], c["A"], c["Ds"], c["dt_bias"], True)
+        y2, pooled = ops.merge_norm_gate(ys, xz[:, C:], c["on_w"], c["on_b"], C, H, W, in_place_order=True)
+        return _block_tail(c, x3, y2, pooled, B, C, H, W)
     # delta (dt_proj o x_proj), B, C of the four directions from one GEMM on the un-permuted x
     dbl = ops.pixlin(xc, c["w_big"])  # (B, 4*(C+2N), L)
     dbl4 = dbl.view(B, 4, C + 2 * N, L)
@@ -81,6 +96,11 @@ def block_forward(block, x: torch.Tensor) -> torch.Tensor:
     ys, _ = ops.selective_scan_fwd(xs.view(B, 4 * C, L), dts.view(B, 4 * C, L), c["A"], bc[:, :, :N], bc[:, :, N:], c["Ds"],
                                    c["dt_bias"], True, need_ckpt=False)
     y2, pooled = ops.merge_norm_gate(ys.view(B, 4, C, L), xz[:, C:], c["on_w"], c["on_b"], C, H, W)
+    return _block_tail(c, x3, y2, pooled, B, C, H, W)
+
+
+def _block_tail(c, x3, y2, pooled, B, C, H, W):
+    L = H * W
     cg = ops.channel_branch(pooled, 1.0 / L, c["ch"], C)
     x1 = ops.pixlin(y2, c["w_out"], c["b_out"], residual=x3, gate=cg, gate_mode=c["gate_mode"])
     t = ops.pixlin(x1, c["w_pin"], c["b_pin"], ln=c["ln2"])

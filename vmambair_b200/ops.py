@@ -205,14 +205,46 @@ def cross_scan(srcs, rows, H, W):
     return out
 
 
-def merge_norm_gate(ys, z, ln_w, ln_b, C_, H, W):
+def transpose_hw(x, H, W):
+    """x: (B, C, H*W) contiguous -> (B, C, W*H) with every plane transposed."""
+    assert x.is_contiguous()
+    out = torch.empty_like(x)
+    a = _lib.TransposeArgs(_ptr(x), _ptr(out), x.shape[0] * x.shape[1], H, W, _DT[x.dtype])
+    _run("vmb_transpose_hw", a, x, "transpose")
+    return out
+
+
+def selective_scan_fwd_grouped(us, deltas, Bs, Cs, revs, A, D, delta_bias, delta_softplus=True):
+    """Direction-aware forward: group g reads us[g] (B,R,L), deltas[g] (B,R,L), Bs[g]/Cs[g] (B,N,L) (views sharing
+    strides) and walks them backwards when revs[g]; returns (B, G, R, L) with group g written in ITS SOURCE's memory order."""
+    G = len(us)
+    b, R, L = us[0].shape
+    N = A.shape[1]
+    for lst in (us, deltas, Bs, Cs):
+        for t in lst:
+            assert t.stride() == lst[0].stride() and t.stride(2) == 1 and t.dtype == us[0].dtype
+    out = torch.empty((b, G, R, L), dtype=us[0].dtype, device=us[0].device)
+    arr = lambda lst: (C.c_void_p * 4)(*([t.data_ptr() for t in lst] + [0] * (4 - G)))
+    outs = [out[:, g] for g in range(G)]
+    a = _lib.ScanGroupedArgs(
+        arr(us), arr(deltas), arr(Bs), arr(Cs), arr(outs), (C.c_int * 4)(*(list(map(int, revs)) + [0] * (4 - G))),
+        _ptr(A), _ptr(D), _ptr(delta_bias), b, G * R, L, N, G,
+        us[0].stride(0), us[0].stride(1), deltas[0].stride(0), deltas[0].stride(1), out.stride(0), out.stride(2),
+        Bs[0].stride(0), Bs[0].stride(1), Cs[0].stride(0), Cs[0].stride(1), int(bool(delta_softplus)), _DT[us[0].dtype])
+    es = us[0].element_size()
+    nbytes = es * b * L * (G * R + G * R + G * R + 2 * G * N)  # every operand / result once
+    _run("vmb_selective_scan_fwd_grouped", a, us[0], "scan_fwd", nbytes)
+    return out
+
+
+def merge_norm_gate(ys, z, ln_w, ln_b, C_, H, W, in_place_order=False):
     """ys: (B,4,C,L) contiguous; z: (B,C,L) view -> (y2 (B,C,L), pooled sums (B,C) fp32)."""
     B = ys.shape[0]
     assert ys.is_contiguous() and z.stride(2) == 1
     y2 = torch.empty((B, C_, H * W), dtype=ys.dtype, device=ys.device)
     pooled = torch.zeros((B, C_), dtype=torch.float32, device=ys.device)
     a = _lib.MergeArgs(_ptr(ys), _ptr(z), _ptr(ln_w), _ptr(ln_b), _ptr(y2), _ptr(pooled), B, C_, H, W,
-                       z.stride(0), z.stride(1), _DT[ys.dtype])
+                       z.stride(0), z.stride(1), _DT[ys.dtype], int(in_place_order))
     _run("vmb_merge_norm_gate", a, ys, "merge")
     return y2, pooled
 
