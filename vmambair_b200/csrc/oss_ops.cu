@@ -338,18 +338,44 @@ __global__ void __launch_bounds__(256) channel_branch_kernel(const ChannelParams
         const bool act = n < N;
         const float A = act ? -__expf(p.Ac_logs[row * N + n]) * kLog2e : 0.f;
         const float Dv = p.Dsc[row];
+        const float* __restrict__ dtr = sDt + (k * dc + j) * C;
+        const float* __restrict__ Br = sDbl + (k * RN + Rc + (act ? n : 0)) * C;
+        const float* __restrict__ Cr = sDbl + (k * RN + Rc + N + (act ? n : 0)) * C;
+        float* __restrict__ yr = sY + (k * dc + j) * C;
         float h = 0.f;
-        for (int l = 0; l < C; ++l) {
-            const int ls = k ? C - 1 - l : l;
-            const float dt = sDt[(k * dc + j) * C + l];
-            const float u = sSeq[j * C + ls];
-            const float Bv = act ? sDbl[(k * RN + Rc + n) * C + l] : 0.f;
-            const float Cv = act ? sDbl[(k * RN + Rc + N + n) * C + l] : 0.f;
-            h = fmaf(ex2(dt * A), h, dt * u * Bv);
-            float y = h * Cv;
+        int l = 0;
+        // 4 positions per iteration: the recurrence is sequential, the four 16-lane reductions run interleaved
+        for (; l + 4 <= C; l += 4) {
+            float dt[4], u[4], a[4], y[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                dt[i] = dtr[l + i];
+                u[i] = sSeq[j * C + (k ? C - 1 - (l + i) : l + i)];
+                a[i] = ex2(dt[i] * A);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                h = fmaf(a[i], h, act ? dt[i] * u[i] * Br[l + i] : 0.f);
+                y[i] = act ? h * Cr[l + i] : 0.f;
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) y[i] += __shfl_xor_sync(0xffffffffu, y[i], o, 16);
+            }
+            if (n == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) yr[l + i] = fmaf(Dv, u[i], y[i]);
+            }
+        }
+        for (; l < C; ++l) {
+            const float dt = dtr[l];
+            const float u = sSeq[j * C + (k ? C - 1 - l : l)];
+            h = fmaf(ex2(dt * A), h, act ? dt * u * Br[l] : 0.f);
+            float y = act ? h * Cr[l] : 0.f;
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o, 16);
-            if (n == 0) sY[(k * dc + j) * C + l] = fmaf(Dv, u, y);
+            if (n == 0) yr[l] = fmaf(Dv, u, y);
         }
     }
     __syncthreads();

@@ -277,8 +277,8 @@ __global__ void __launch_bounds__(PL2_THREADS) pixlin_mma_kernel(const PixlinPar
     constexpr int OP = WN + 4;
     in_t* sX = reinterpret_cast<in_t*>(smem_raw);                    // [KC][XP]
     in_t* sW0 = sX + KC * XP;                                        // [2][64][WP]
-    float* sOut = reinterpret_cast<float*>(sW0 + 2 * PL_MT * WP);    // [8 warps][32][OP]
-    float* sStat = sOut + 8 * 32 * OP;                               // [256]
+    float* sOut = reinterpret_cast<float*>(sW0 + 2 * PL_MT * WP);    // [8 warps][16][OP]
+    float* sStat = sOut + 8 * 16 * OP;                               // [256]
     const int b = blockIdx.z, p0 = blockIdx.x * PT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wm = warp >> 2, wn = warp & 3;                         // 2 x 4 warp grid
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(PL2_THREADS) pixlin_mma_kernel(const PixlinPar
         prologue2<in_t, PT>(sX, XP, p, b, p.K, sStat);
     }
     float acc[2][NT8][4];
-    float* myOut = sOut + warp * 32 * OP;
+    float* myOut = sOut + warp * 16 * OP;
     const in_t* __restrict__ res = p.residual ? reinterpret_cast<const in_t*>(p.residual) + (int64_t)b * p.r_bs : nullptr;
     out_t* __restrict__ ob = reinterpret_cast<out_t*>(p.out) + (int64_t)b * p.o_bs;
 
@@ -343,43 +343,45 @@ __global__ void __launch_bounds__(PL2_THREADS) pixlin_mma_kernel(const PixlinPar
                 for (int nj = 0; nj < NT8; ++nj) MmaType<in_t>::mma(acc[mi][nj], af[mi], bf[nj]);
         }
         if (s % nkc != nkc - 1) continue;
-        // ---- epilogue of this output-channel tile: warp-private smem patch -> row-contiguous stores ----
-        __syncwarp();
+        // ---- epilogue of this output-channel tile: warp-private smem patch (16 rows at a time) -> row-contiguous stores ----
+        constexpr int G = 8, GPR = WN / G;  // 8-pixel groups per row
 #pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
+        for (int mi = 0; mi < 2; ++mi) {
+            __syncwarp();
 #pragma unroll
             for (int nj = 0; nj < NT8; ++nj) {
-                const int row = mi * 16 + (lane >> 2), col = nj * 8 + 2 * (lane & 3);
+                const int row = lane >> 2, col = nj * 8 + 2 * (lane & 3);
                 *reinterpret_cast<float2*>(&myOut[row * OP + col]) = make_float2(acc[mi][nj][0], acc[mi][nj][1]);
                 *reinterpret_cast<float2*>(&myOut[(row + 8) * OP + col]) = make_float2(acc[mi][nj][2], acc[mi][nj][3]);
             }
-        __syncwarp();
-        constexpr int G = 8, GPR = WN / G;  // 8-pixel groups per row
-        for (int it = lane; it < 32 * GPR; it += 32) {
-            const int row = it / GPR, q = (it % GPR) * G;
-            const int mg = m0 + wm * 32 + row;
-            const int pg = p0 + wn * WN + q;
-            const int valid = p.P - pg;
-            if (mg >= p.M || valid <= 0) continue;
-            float v[G];
-            const float bs = p.bias ? p.bias[mg] : 0.f;
-            const bool act = mg >= p.act_from && mg < p.act_to;
+            __syncwarp();
 #pragma unroll
-            for (int i = 0; i < G; ++i) {
-                const float t = myOut[row * OP + q + i] + bs;
-                v[i] = act ? silu_f(t) : t;
+            for (int it = lane; it < 16 * GPR; it += 32) {
+                const int row = it / GPR, q = (it % GPR) * G;
+                const int mg = m0 + wm * 32 + mi * 16 + row;
+                const int pg = p0 + wn * WN + q;
+                const int valid = p.P - pg;
+                if (mg >= p.M || valid <= 0) continue;
+                float v[G];
+                const float bs = p.bias ? p.bias[mg] : 0.f;
+                const bool act = mg >= p.act_from && mg < p.act_to;
+#pragma unroll
+                for (int i = 0; i < G; ++i) {
+                    const float t = myOut[row * OP + q + i] + bs;
+                    v[i] = act ? silu_f(t) : t;
+                }
+                if (res) {
+                    float rr[G];
+                    constexpr int VI = Vec<in_t>::N;
+#pragma unroll
+                    for (int j = 0; j < G / VI; ++j) load_vec<in_t>(res + (int64_t)mg * p.r_cs + pg + j * VI, rr + j * VI, valid - j * VI, p.vec_ok);
+#pragma unroll
+                    for (int i = 0; i < G; ++i) v[i] += rr[i];
+                }
+                constexpr int VO = Vec<out_t>::N;
+#pragma unroll
+                for (int j = 0; j < G / VO; ++j) store_vec<out_t>(ob + (int64_t)mg * p.o_cs + pg + j * VO, v + j * VO, valid - j * VO, p.vec_ok);
             }
-            if (res) {
-                float rr[G];
-                constexpr int VI = Vec<in_t>::N;
-#pragma unroll
-                for (int j = 0; j < G / VI; ++j) load_vec<in_t>(res + (int64_t)mg * p.r_cs + pg + j * VI, rr + j * VI, valid - j * VI, p.vec_ok);
-#pragma unroll
-                for (int i = 0; i < G; ++i) v[i] += rr[i];
-            }
-            constexpr int VO = Vec<out_t>::N;
-#pragma unroll
-            for (int j = 0; j < G / VO; ++j) store_vec<out_t>(ob + (int64_t)mg * p.o_cs + pg + j * VO, v + j * VO, valid - j * VO, p.vec_ok);
         }
     }
 }
@@ -440,7 +442,7 @@ static size_t pixlin_smem(int K, int elt, int PT = 64) {
     const int kpad = (K + 15) / 16 * 16;
     if (elt == 2) {
         const int KC = kpad < PL2_KC ? kpad : PL2_KC;
-        return (size_t)2 * (KC * (PT + 8) + 2 * PL_MT * (KC + 8)) + 4 * (8 * 32 * (PT / 4 + 4) + 256);
+        return (size_t)2 * (KC * (PT + 8) + 2 * PL_MT * (KC + 8)) + 4 * (8 * 16 * (PT / 4 + 4) + 256);
     }
     const int KC = kpad < PL_KC / 2 ? kpad : PL_KC / 2;
     return (size_t)4 * (KC * (PL_PT + 4) + PL_MT * (KC + 1) + PL_MT * (PL_PT + 4) + 2 * PL_PT);
