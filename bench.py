@@ -154,7 +154,8 @@ def run_infer(args):
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
     B = B_PER_GPU_INFER
-    eng = InferenceEngine(build_net("light"), B, H, W, dtype=torch.bfloat16, device=dev)
+    chains = int(os.environ.get("VMB_CHAINS", "1"))
+    eng = InferenceEngine(build_net("light"), B, H, W, dtype=torch.bfloat16, device=dev, chains=chains)
     g = torch.Generator().manual_seed(1234 + rank)
     x_host = torch.rand(B, 3, H, W, generator=g).to(torch.bfloat16).pin_memory()
     eng.x_dev.copy_(x_host)
@@ -220,7 +221,7 @@ def run_infer(args):
         "lq_mpix_per_s": round(value * H * W / 1e6, 3),
         "config": {"workload": "VmambaIR-light (MambaSISR6 [6,2,2,1]+6, 10.5M params) SRx4 inference, B=8 x 3x64x64 LQ per GPU",
                    "global_batch": world * B, "parallelism": f"batch-sharded x{world}, no collective",
-                   "l2": "256 MiB memset between timed steps", "graph": "CUDA graph replay",
+                   "l2": "256 MiB memset between timed steps", "graph": f"CUDA graph replay, {chains} concurrent sub-batch chains",
                    "path": "fused" if os.environ.get("VMB_PATH", "") != "compose" else "compose"},
         "e2e": {"value": round(world * B * K / e2e_s, 2), "unit": "images/s",
                 "h2d_bytes_per_step": int(x_host.numel() * x_host.element_size()),

@@ -249,18 +249,22 @@ __device__ __forceinline__ void stage_w2(in_t* __restrict__ sW, int WP, const Pi
     constexpr int V = Vec<in_t>::N;
     const in_t* __restrict__ w = reinterpret_cast<const in_t*>(p.w);
     const int groups = kpad / V;
-    for (int it = threadIdx.x; it < PL_MT * groups; it += PL2_THREADS) {
-        const int m = it / groups, k = (it % groups) * V;
-        in_t* dst = sW + m * WP + k;
-        if (p.w_vec) {
-            const bool ok = m0 + m < p.M;
-            cp_async16_pl(dst, ok ? (const void*)(w + (int64_t)(m0 + m) * p.w_ld + k0 + k) : (const void*)w, ok ? 16 : 0);
-        } else {
-            in_t tmp[V];
+    // 16 x 16 thread grid over (rows, 16-byte groups): no integer division in the loop
+    const int tm = threadIdx.x >> 4, tk = threadIdx.x & 15;
+    for (int m = tm; m < PL_MT; m += 16) {
+        const bool row_ok = m0 + m < p.M;
+        const in_t* __restrict__ wrow = w + (int64_t)(row_ok ? m0 + m : 0) * p.w_ld + k0;
+        for (int kg = tk; kg < groups; kg += 16) {
+            const int k = kg * V;
+            in_t* dst = sW + m * WP + k;
+            if (p.w_vec) {
+                cp_async16_pl(dst, wrow + k, row_ok ? 16 : 0);
+            } else {
+                in_t tmp[V];
 #pragma unroll
-            for (int i = 0; i < V; ++i)
-                tmp[i] = (m0 + m < p.M && k + i < kc) ? w[(int64_t)(m0 + m) * p.w_ld + k0 + k + i] : from_f32<in_t>(0.f);
-            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(tmp);
+                for (int i = 0; i < V; ++i) tmp[i] = (row_ok && k + i < kc) ? wrow[k + i] : from_f32<in_t>(0.f);
+                *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(tmp);
+            }
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -363,12 +367,20 @@ __global__ void __launch_bounds__(PL2_THREADS) pixlin_mma_kernel(const PixlinPar
                 const int valid = p.P - pg;
                 if (mg >= p.M || valid <= 0) continue;
                 float v[G];
-                const float bs = p.bias ? p.bias[mg] : 0.f;
-                const bool act = mg >= p.act_from && mg < p.act_to;
+                {
+                    const float4 a0 = *reinterpret_cast<const float4*>(&myOut[row * OP + q]);
+                    const float4 a1 = *reinterpret_cast<const float4*>(&myOut[row * OP + q + 4]);
+                    v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w;
+                    v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+                }
+                if (p.bias) {
+                    const float bs = p.bias[mg];
 #pragma unroll
-                for (int i = 0; i < G; ++i) {
-                    const float t = myOut[row * OP + q + i] + bs;
-                    v[i] = act ? silu_f(t) : t;
+                    for (int i = 0; i < G; ++i) v[i] += bs;
+                }
+                if (mg >= p.act_from && mg < p.act_to) {
+#pragma unroll
+                    for (int i = 0; i < G; ++i) v[i] = silu_f(v[i]);
                 }
                 if (res) {
                     float rr[G];
@@ -453,7 +465,7 @@ static int launch2(K kern, const PixlinParams& p, size_t smem, int PT, cudaStrea
     if (smem > 48 * 1024) VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ptiles = (p.P + PT - 1) / PT, mtiles = (p.M + PL_MT - 1) / PL_MT;
     int msplit = 1;
-    while (msplit < mtiles && (long)ptiles * p.B * msplit < 148L * 2) ++msplit;
+    while (msplit < mtiles && (long)ptiles * p.B * msplit < 148L * 3 / 2) ++msplit;
     dim3 grid(ptiles, msplit, p.B);
     kern<<<grid, PL2_THREADS, smem, stream>>>(p);
     VMB_CUDA(cudaGetLastError());
