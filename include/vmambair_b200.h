@@ -146,16 +146,19 @@ typedef struct { const void* x; void* out; int planes, H, W; int dtype; } vmb_tr
 int vmb_transpose_hw(const vmb_transpose_args* a, void* stream);
 
 /* inverse orders + 4-way fp32 sum (:427-430 / CrossMerge) + out_norm (:433) + gate y*SiLU(z) (:493) +
- * per-(b,c) sums of the result for AdaptiveAvgPool2d (:441; `pooled` fp32 (B,C), caller zero-fills). */
+ * per-(b,c) sums of the result for AdaptiveAvgPool2d (:441; `pooled` fp32 (B,C), fully written).
+ * workspace: vmb_merge_workspace_bytes() bytes of device scratch (fp32 merged values + per-pixel statistics). */
 typedef struct {
     const void* ys; const void* z; const float* ln_w; const float* ln_b; void* y2; float* pooled;
     int batch, C, H, W;
     int64_t z_bs, z_cs;
     int dtype;
+    void* workspace;
     int in_place_order; /* 0: ys[k] in scan order (k=2,3 reversed); 1: ys[0],ys[2] in natural (H,W) pixel order and
                            ys[1],ys[3] in transposed (W,H) pixel order (outputs of vmb_selective_scan_fwd_grouped) */
 } vmb_merge_args;
 int vmb_merge_norm_gate(const vmb_merge_args* a, void* stream);
+int64_t vmb_merge_workspace_bytes(int batch, int C, int H, int W);
 
 /* the channel-direction OSS for one image per CTA (cforward_corev1 :438-483; Mamber32/33 and RealSR variants):
  * pooled means -> conv_cin -> xc_proj / dtc_proj -> bidirectional selective scan over L=C -> conv_cout ->

@@ -71,7 +71,7 @@ class MergeArgs(C.Structure):
     _fields_ = [
         ("ys", vp), ("z", vp), ("ln_w", vp), ("ln_b", vp), ("y2", vp), ("pooled", vp),
         ("batch", C.c_int), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int),
-        ("z_bs", i64), ("z_cs", i64), ("dtype", C.c_int), ("in_place_order", C.c_int),
+        ("z_bs", i64), ("z_cs", i64), ("dtype", C.c_int), ("workspace", vp), ("in_place_order", C.c_int),
     ]
 
 
@@ -111,6 +111,7 @@ SYMBOLS = {
     "vmb_dwconv3x3": (C.c_int, [C.POINTER(DwconvArgs), vp]),
     "vmb_cross_scan": (C.c_int, [C.POINTER(CrossScanArgs), vp]),
     "vmb_merge_norm_gate": (C.c_int, [C.POINTER(MergeArgs), vp]),
+    "vmb_merge_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "vmb_transpose_hw": (C.c_int, [C.POINTER(TransposeArgs), vp]),
     "vmb_selective_scan_fwd_grouped": (C.c_int, [C.POINTER(ScanGroupedArgs), vp]),
     "vmb_channel_branch": (C.c_int, [C.POINTER(ChannelArgs), vp]),

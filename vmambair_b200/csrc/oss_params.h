@@ -27,6 +27,7 @@ struct MergeParams {
     int B, C, H, W;
     int64_t z_bs, z_cs;
     int in_place_order;
+    void* ws;  // fp32 scratch: B*C*L merged values + 2*B*L per-pixel statistics
 };
 struct TransposeParams {
     const void* x; void* out;
