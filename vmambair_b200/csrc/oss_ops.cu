@@ -339,9 +339,10 @@ int merge_launch(const MergeParams& p, int dtype, cudaStream_t stream) {
 __global__ void __launch_bounds__(256) channel_branch_kernel(const ChannelParams p) {
     extern __shared__ float sm[];
     const int C = p.C, dc = p.dc, Rc = p.Rc, N = p.N, RN = Rc + 2 * N;
+    const int CP = C | 1;                // odd row pitch of sDbl: the 16 state lanes of the scan read 16 different rows
     float* sSeq = sm;                    // [dc][C]     xc
     float* sDbl = sSeq + dc * C;         // [2][RN][C]  xc_dbl per direction (direction order)
-    float* sDt = sDbl + 2 * RN * C;      // [2][dc][C]  softplus'ed dt
+    float* sDt = sDbl + 2 * RN * CP;     // [2][dc][C]  softplus'ed dt
     float* sY = sDt + 2 * dc * C;        // [2][dc][C]  scan outputs (direction order)
     float* sOut = sY + 2 * dc * C;       // [C]
     float* sRed = sOut + C;              // [64]
@@ -374,14 +375,14 @@ __global__ void __launch_bounds__(256) channel_branch_kernel(const ChannelParams
         const int ls = k ? C - 1 - l : l;
         float a = 0.f;
         for (int j = 0; j < dc; ++j) a = fmaf(sXp[(k * RN + c) * dc + j], sSeq[j * C + ls], a);
-        sDbl[i] = a;
+        sDbl[(k * RN + c) * CP + l] = a;
     }
     __syncthreads();
     // dt[k][j][l] = softplus(sum_r Wdt[k][j][r] * dbl[k][r][l] + bias)
     for (int i = tid; i < 2 * dc * C; i += 256) {
         const int k = i / (dc * C), j = (i / C) % dc, l = i % C;
         float a = sDb[k * dc + j];
-        for (int r = 0; r < Rc; ++r) a = fmaf(sDw[(k * dc + j) * Rc + r], sDbl[(k * RN + r) * C + l], a);
+        for (int r = 0; r < Rc; ++r) a = fmaf(sDw[(k * dc + j) * Rc + r], sDbl[(k * RN + r) * CP + l], a);
         sDt[i] = softplus_f(a);
     }
     __syncthreads();
@@ -394,8 +395,8 @@ __global__ void __launch_bounds__(256) channel_branch_kernel(const ChannelParams
         const float A = act ? -__expf(p.Ac_logs[row * N + n]) * kLog2e : 0.f;
         const float Dv = p.Dsc[row];
         const float* __restrict__ dtr = sDt + (k * dc + j) * C;
-        const float* __restrict__ Br = sDbl + (k * RN + Rc + (act ? n : 0)) * C;
-        const float* __restrict__ Cr = sDbl + (k * RN + Rc + N + (act ? n : 0)) * C;
+        const float* __restrict__ Br = sDbl + (k * RN + Rc + (act ? n : 0)) * CP;
+        const float* __restrict__ Cr = sDbl + (k * RN + Rc + N + (act ? n : 0)) * CP;
         float* __restrict__ yr = sY + (k * dc + j) * C;
         float h = 0.f;
         int l = 0;
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__(256) channel_branch_kernel(const ChannelParams
 int channel_launch(const ChannelParams& p, cudaStream_t stream) {
     VMB_CHECK(p.N <= 16, "channel branch: dstate <= 16 supported (got %d)", p.N);
     const int RN = p.Rc + 2 * p.N;
-    const size_t smem = sizeof(float) * ((size_t)p.dc * p.C + 2 * RN * p.C + 4 * p.dc * p.C + p.C + 64 + 2 * RN * p.dc +
+    const size_t smem = sizeof(float) * ((size_t)p.dc * p.C + 2 * RN * (p.C | 1) + 4 * p.dc * p.C + p.C + 64 + 2 * RN * p.dc +
                                          2 * p.dc * p.Rc + 2 * p.dc + 3 * p.dc + 1);
     VMB_CHECK(smem <= 227 * 1024, "channel branch: C=%d too large", p.C);
     if (smem > 48 * 1024)
