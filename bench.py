@@ -95,8 +95,9 @@ def cpu_oracle_images_per_s(steps, warmup, threads=None):
     """The reference path on the host CPU: oracle port (oracle/oss_ref.py + C scan), one image per step."""
     from oracle import oss_ref, cscan
     cscan.build()
-    if threads:
-        torch.set_num_threads(threads)
+    threads = threads or os.cpu_count() // 2 or 1  # physical cores; torchrun would otherwise pin OMP_NUM_THREADS=1
+    torch.set_num_threads(threads)
+    cscan.set_threads(threads)
     net = build_net("light")
     sd = {k: v.detach().float() for k, v in net.state_dict().items()}
     g = torch.Generator().manual_seed(1)

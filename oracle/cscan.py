@@ -33,6 +33,10 @@ def lib():
     return _lib
 
 
+def set_threads(n: int):
+    lib().scan_ref_set_threads(int(n))
+
+
 def _f32(t):
     if t is None:
         return None

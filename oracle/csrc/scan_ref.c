@@ -15,6 +15,18 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline must use every host core it can */
+void scan_ref_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 static inline float softplus_f(float x) { return x <= 20.f ? log1pf(expf(x)) : x; }
 static inline double softplus_d(double x) { return x <= 20.0 ? log1p(exp(x)) : x; }
 
