@@ -199,46 +199,74 @@ __device__ __forceinline__ void stage_x2(in_t* __restrict__ sX, int XP, const Pi
     }
 }
 
+template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t v);
+template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t v) {
+    return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t v) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+
+// LayerNorm / gate prologue on the resident tile, two adjacent pixels per thread (packed 32-bit smem accesses)
 template <typename in_t, int PT>
 __device__ __forceinline__ void prologue2(in_t* __restrict__ sX, int XP, const PixlinParams& p, int b, int K, float* sStat) {
-    // 256 threads: PT pixels x (256/PT) K-slices
-    constexpr int SL = PL2_THREADS / PT;
+    constexpr int PP = PT / 2;               // pixel pairs
+    constexpr int SL = PL2_THREADS / PP;     // K slices (4 or 8)
+    const int px = (threadIdx.x % PP) * 2, sl = threadIdx.x / PP;
+    float2* st0 = reinterpret_cast<float2*>(sStat);   // [SL][PP]
+    float2* st1 = st0 + SL * PP;                       // [SL][PP]
     if (p.ln_mode) {
         __syncthreads();
-        const int px = threadIdx.x % PT, sl = threadIdx.x / PT;
-        float s = 0.f;
-        for (int k = sl; k < K; k += SL) s += to_f32<in_t>(sX[k * XP + px]);
-        sStat[sl * PT + px] = s;
-        __syncthreads();
-        float mu = 0.f;
-#pragma unroll
-        for (int i = 0; i < SL; ++i) mu += sStat[i * PT + px];
-        mu /= K;
-        __syncthreads();
-        float v = 0.f;
+        float2 s = make_float2(0.f, 0.f);
         for (int k = sl; k < K; k += SL) {
-            const float dlt = to_f32<in_t>(sX[k * XP + px]) - mu;
-            v += dlt * dlt;
+            const float2 v = unpack2<in_t>(*reinterpret_cast<const uint32_t*>(sX + k * XP + px));
+            s.x += v.x;
+            s.y += v.y;
         }
-        sStat[sl * PT + px] = v;
+        st0[sl * PP + px / 2] = s;
         __syncthreads();
-        float var = 0.f;
+        float2 mu = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < SL; ++i) var += sStat[i * PT + px];
-        const float rstd = rsqrtf(var / K + 1e-5f);
+        for (int i = 0; i < SL; ++i) {
+            const float2 t = st0[i * PP + px / 2];
+            mu.x += t.x;
+            mu.y += t.y;
+        }
+        mu.x /= K;
+        mu.y /= K;
+        float2 v2 = make_float2(0.f, 0.f);
         for (int k = sl; k < K; k += SL) {
-            float xv = to_f32<in_t>(sX[k * XP + px]);
-            xv = p.ln_mode == 1 ? (xv - mu) * rstd * p.ln_w[k] + p.ln_b[k] : xv * rstd * p.ln_w[k];
-            sX[k * XP + px] = from_f32<in_t>(xv);
+            const float2 v = unpack2<in_t>(*reinterpret_cast<const uint32_t*>(sX + k * XP + px));
+            v2.x = fmaf(v.x - mu.x, v.x - mu.x, v2.x);
+            v2.y = fmaf(v.y - mu.y, v.y - mu.y, v2.y);
+        }
+        st1[sl * PP + px / 2] = v2;
+        __syncthreads();
+        float2 var = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < SL; ++i) {
+            const float2 t = st1[i * PP + px / 2];
+            var.x += t.x;
+            var.y += t.y;
+        }
+        const float r0 = rsqrtf(var.x / K + 1e-5f), r1 = rsqrtf(var.y / K + 1e-5f);
+        const bool wb = p.ln_mode == 1;
+        const float m0 = wb ? mu.x : 0.f, m1 = wb ? mu.y : 0.f;
+        for (int k = sl; k < K; k += SL) {
+            uint32_t* ptr = reinterpret_cast<uint32_t*>(sX + k * XP + px);
+            const float2 v = unpack2<in_t>(*ptr);
+            const float w = p.ln_w[k] , bb = wb ? p.ln_b[k] : 0.f;
+            *ptr = pack2<in_t>(fmaf((v.x - m0) * r0, w, bb), fmaf((v.y - m1) * r1, w, bb));
         }
     }
     if (p.gate_mode) {
         __syncthreads();
         const float* __restrict__ g = p.gate + (int64_t)b * p.g_bs;
-        for (int it = threadIdx.x; it < K * PT; it += PL2_THREADS) {
-            const int k = it / PT, q = it % PT;
-            const float xv = to_f32<in_t>(sX[k * XP + q]);
-            sX[k * XP + q] = from_f32<in_t>(p.gate_mode == 1 ? fmaf(xv, g[k], xv) : xv + g[k]);
+        for (int k = sl; k < K; k += SL) {
+            uint32_t* ptr = reinterpret_cast<uint32_t*>(sX + k * XP + px);
+            const float2 v = unpack2<in_t>(*ptr);
+            const float gk = g[k];
+            *ptr = p.gate_mode == 1 ? pack2<in_t>(fmaf(v.x, gk, v.x), fmaf(v.y, gk, v.y)) : pack2<in_t>(v.x + gk, v.y + gk);
         }
     }
 }
@@ -282,7 +310,7 @@ __global__ void __launch_bounds__(PL2_THREADS) pixlin_mma_kernel(const PixlinPar
     in_t* sX = reinterpret_cast<in_t*>(smem_raw);                    // [KC][XP]
     in_t* sW0 = sX + KC * XP;                                        // [2][64][WP]
     float* sOut = reinterpret_cast<float*>(sW0 + 2 * PL_MT * WP);    // [8 warps][16][OP]
-    float* sStat = sOut + 8 * 16 * OP;                               // [256]
+    float* sStat = sOut + 8 * 16 * OP;                               // [1024]
     const int b = blockIdx.z, p0 = blockIdx.x * PT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wm = warp >> 2, wn = warp & 3;                         // 2 x 4 warp grid
@@ -347,7 +375,38 @@ __global__ void __launch_bounds__(PL2_THREADS) pixlin_mma_kernel(const PixlinPar
                 for (int nj = 0; nj < NT8; ++nj) MmaType<in_t>::mma(acc[mi][nj], af[mi], bf[nj]);
         }
         if (s % nkc != nkc - 1) continue;
-        // ---- epilogue of this output-channel tile: warp-private smem patch (16 rows at a time) -> row-contiguous stores ----
+        // ---- epilogue of this output-channel tile ----
+        if constexpr (sizeof(out_t) == 2) {
+            if (p.vec_ok) {  // straight from the accumulators: each thread owns 2 adjacent pixels of 16 (row, n8) fragments
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int mg = m0 + wm * 32 + mi * 16 + hf * 8 + (lane >> 2);
+                        if (mg >= p.M) continue;
+                        const float bs = p.bias ? p.bias[mg] : 0.f;
+                        const bool act = mg >= p.act_from && mg < p.act_to;
+#pragma unroll
+                        for (int nj = 0; nj < NT8; ++nj) {
+                            const int pg = p0 + wn * WN + nj * 8 + 2 * (lane & 3);
+                            if (pg >= p.P) continue;
+                            float v0 = acc[mi][nj][hf * 2] + bs, v1 = acc[mi][nj][hf * 2 + 1] + bs;
+                            if (act) {
+                                v0 = silu_f(v0);
+                                v1 = silu_f(v1);
+                            }
+                            if (res) {
+                                const float2 r2 = unpack2<in_t>(*reinterpret_cast<const uint32_t*>(res + (int64_t)mg * p.r_cs + pg));
+                                v0 += r2.x;
+                                v1 += r2.y;
+                            }
+                            *reinterpret_cast<uint32_t*>(ob + (int64_t)mg * p.o_cs + pg) = pack2<out_t>(v0, v1);
+                        }
+                    }
+                continue;
+            }
+        }
+        // generic path: warp-private smem patch (16 rows at a time) -> row-contiguous stores
         constexpr int G = 8, GPR = WN / G;  // 8-pixel groups per row
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi) {
@@ -454,7 +513,7 @@ static size_t pixlin_smem(int K, int elt, int PT = 64) {
     const int kpad = (K + 15) / 16 * 16;
     if (elt == 2) {
         const int KC = kpad < PL2_KC ? kpad : PL2_KC;
-        return (size_t)2 * (KC * (PT + 8) + 2 * PL_MT * (KC + 8)) + 4 * (8 * 16 * (PT / 4 + 4) + 256);
+        return (size_t)2 * (KC * (PT + 8) + 2 * PL_MT * (KC + 8)) + 4 * (8 * 16 * (PT / 4 + 4) + 1024);
     }
     const int KC = kpad < PL_KC / 2 ? kpad : PL_KC / 2;
     return (size_t)4 * (KC * (PL_PT + 4) + PL_MT * (KC + 1) + PL_MT * (PL_PT + 4) + 2 * PL_PT);
