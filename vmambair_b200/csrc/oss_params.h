@@ -9,7 +9,8 @@ struct PixlinParams {
     const float* ln_w; const float* ln_b; const float* gate;
     int ln_mode, gate_mode, act_from, act_to, B, K, M, P;
     int64_t x_bs, x_cs, r_bs, r_cs, o_bs, o_cs, g_bs, w_ld;
-    bool vec_ok, w_vec;
+    bool vec_ok, w_vec, w_all;
+    int w_tiles;  // weight-tile buffers in smem (2 = double buffer, or every tile of the CTA when w_all)
 };
 struct DwParams {
     const void* x; const float* w; const float* bias; void* out;

@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(PL2_THREADS) pixlin_mma_kernel(const PixlinPar
     constexpr int OP = WN + 4;
     in_t* sX = reinterpret_cast<in_t*>(smem_raw);                    // [KC][XP]
     in_t* sW0 = sX + KC * XP;                                        // [2][64][WP]
-    float* sOut = reinterpret_cast<float*>(sW0 + 2 * PL_MT * WP);    // [8 warps][16][OP]
+    float* sOut = reinterpret_cast<float*>(sW0 + p.w_tiles * PL_MT * WP);  // [8 warps][16][OP]
     float* sStat = sOut + 8 * 16 * OP;                               // [1024]
     const int b = blockIdx.z, p0 = blockIdx.x * PT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -322,7 +322,12 @@ __global__ void __launch_bounds__(PL2_THREADS) pixlin_mma_kernel(const PixlinPar
 
     auto step_m0 = [&](int s) { return ((int)blockIdx.y + (s / nkc) * (int)gridDim.y) * PL_MT; };
     auto step_k0 = [&](int s) { return (s % nkc) * KC; };
-    if (steps > 0) stage_w2<in_t>(sW0, WP, p, step_m0(0), step_k0(0), min(p.K - step_k0(0), KC), min(kpad_all - step_k0(0), KC));
+    const bool w_all = p.w_all;  // every weight tile of this CTA resident: one batch of copies, no per-tile wait / barrier
+    if (w_all) {
+        for (int s = 0; s < steps; ++s) stage_w2<in_t>(sW0 + s * PL_MT * WP, WP, p, step_m0(s), 0, p.K, kpad_all);
+    } else if (steps > 0) {
+        stage_w2<in_t>(sW0, WP, p, step_m0(0), step_k0(0), min(p.K - step_k0(0), KC), min(kpad_all - step_k0(0), KC));
+    }
     if (resident) {
         stage_x2<in_t, PT>(sX, XP, p, b, p0, 0, p.K, KC);
         prologue2<in_t, PT>(sX, XP, p, b, p.K, sStat);
@@ -335,7 +340,7 @@ __global__ void __launch_bounds__(PL2_THREADS) pixlin_mma_kernel(const PixlinPar
     for (int s = 0; s < steps; ++s) {
         const int m0 = step_m0(s), k0 = step_k0(s);
         const int kpad = min(kpad_all - k0, KC);
-        in_t* sW = sW0 + (s & 1) * PL_MT * WP;
+        in_t* sW = sW0 + (w_all ? s : (s & 1)) * PL_MT * WP;
         if (s % nkc == 0) {
 #pragma unroll
             for (int i = 0; i < 2; ++i)
@@ -348,9 +353,11 @@ __global__ void __launch_bounds__(PL2_THREADS) pixlin_mma_kernel(const PixlinPar
             __syncthreads();  // previous chunk's X fully consumed
             stage_x2<in_t, PT>(sX, XP, p, b, p0, k0, min(p.K - k0, KC), kpad);
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();  // W[s] (and X) visible to all; everyone is done reading the other W buffer
-        if (s + 1 < steps)
+        if (!w_all || s == 0) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();  // W[s] (and X) visible to all; everyone is done reading the other W buffer
+        }
+        if (!w_all && s + 1 < steps)
             stage_w2<in_t>(sW0 + ((s + 1) & 1) * PL_MT * WP, WP, p, step_m0(s + 1), step_k0(s + 1),
                            min(p.K - step_k0(s + 1), KC), min(kpad_all - step_k0(s + 1), KC));
         for (int kk = 0; kk < kpad; kk += 16) {
@@ -509,22 +516,40 @@ __global__ void __launch_bounds__(PL_THREADS) pixlin_f32_kernel(const PixlinPara
     }
 }
 
-static size_t pixlin_smem(int K, int elt, int PT = 64) {
+static size_t pixlin_smem(int K, int elt, int PT = 64, int wtiles = 2) {
     const int kpad = (K + 15) / 16 * 16;
     if (elt == 2) {
         const int KC = kpad < PL2_KC ? kpad : PL2_KC;
-        return (size_t)2 * (KC * (PT + 8) + 2 * PL_MT * (KC + 8)) + 4 * (8 * 16 * (PT / 4 + 4) + 1024);
+        return (size_t)2 * (KC * (PT + 8) + wtiles * PL_MT * (KC + 8)) + 4 * (8 * 16 * (PT / 4 + 4) + 1024);
     }
     const int KC = kpad < PL_KC / 2 ? kpad : PL_KC / 2;
     return (size_t)4 * (KC * (PL_PT + 4) + PL_MT * (KC + 1) + PL_MT * (PL_PT + 4) + 2 * PL_PT);
 }
 
 template <typename K>
-static int launch2(K kern, const PixlinParams& p, size_t smem, int PT, cudaStream_t stream) {
-    if (smem > 48 * 1024) VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+static int launch2(K kern, PixlinParams p, int PT, cudaStream_t stream) {
     const int ptiles = (p.P + PT - 1) / PT, mtiles = (p.M + PL_MT - 1) / PL_MT;
+    const int kpad = (p.K + 15) / 16 * 16;
+    // split the output channels over blockIdx.y (a) until the grid covers the SMs ~1.5x and (b), when K is resident,
+    // until all weight tiles of a CTA fit in <= 64 KB of smem: then they are fetched in one batch (no per-tile wait)
     int msplit = 1;
     while (msplit < mtiles && (long)ptiles * p.B * msplit < 148L * 3 / 2) ++msplit;
+    p.w_all = false;
+    int wtiles = 2;
+    if (kpad <= PL2_KC && p.w_vec) {
+        int ms = msplit;
+        while (ms < mtiles && (size_t)((mtiles + ms - 1) / ms) * PL_MT * (kpad + 8) * 2 > 64 * 1024) ++ms;
+        const int per = (mtiles + ms - 1) / ms;
+        if ((size_t)per * PL_MT * (kpad + 8) * 2 <= 64 * 1024) {
+            msplit = ms;
+            p.w_all = true;
+            wtiles = per;
+        }
+    }
+    p.w_tiles = wtiles;
+    const size_t smem = pixlin_smem(p.K, 2, PT, wtiles);
+    VMB_CHECK(smem <= 227 * 1024, "pixlin: K=%d needs %zu B of shared memory", p.K, smem);
+    if (smem > 48 * 1024) VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ptiles, msplit, p.B);
     kern<<<grid, PL2_THREADS, smem, stream>>>(p);
     VMB_CUDA(cudaGetLastError());
@@ -534,15 +559,13 @@ static int launch2(K kern, const PixlinParams& p, size_t smem, int PT, cudaStrea
 template <typename in_t>
 static int launch_mma(const PixlinParams& p, int out_dtype, cudaStream_t stream) {
     // 128-pixel tiles when there are enough pixels to fill the GPU with them, else 64
-    const bool big = (long)((p.P + 127) / 128) * p.B >= 148 && pixlin_smem(p.K, 2, 128) <= 200 * 1024;
+    const bool big = (long)((p.P + 127) / 128) * p.B >= 148 && pixlin_smem(p.K, 2, 128, 2) <= 100 * 1024;
     const int PT = big ? 128 : 64;
-    const size_t smem = pixlin_smem(p.K, 2, PT);
-    VMB_CHECK(smem <= 227 * 1024, "pixlin: K=%d needs %zu B of shared memory", p.K, smem);
     if (out_dtype == VMB_F32)
-        return big ? launch2(pixlin_mma_kernel<in_t, float, 128>, p, smem, PT, stream)
-                   : launch2(pixlin_mma_kernel<in_t, float, 64>, p, smem, PT, stream);
-    return big ? launch2(pixlin_mma_kernel<in_t, in_t, 128>, p, smem, PT, stream)
-               : launch2(pixlin_mma_kernel<in_t, in_t, 64>, p, smem, PT, stream);
+        return big ? launch2(pixlin_mma_kernel<in_t, float, 128>, p, PT, stream)
+                   : launch2(pixlin_mma_kernel<in_t, float, 64>, p, PT, stream);
+    return big ? launch2(pixlin_mma_kernel<in_t, in_t, 128>, p, PT, stream)
+               : launch2(pixlin_mma_kernel<in_t, in_t, 64>, p, PT, stream);
 }
 
 template <typename K>

@@ -246,6 +246,8 @@ __global__ void __launch_bounds__(32 * WPC, 16 / WPC) scan_fwd_kernel(const Scan
             for (int np = 0; np < 8; ++np) {
                 const int n0 = nt * 16 + 2 * np;
                 const float2 A2 = *reinterpret_cast<const float2*>(&sA[r * npad + n0]);
+                float2* carry = reinterpret_cast<float2*>(&sCarry[r * npad + n0]);
+                const float2 st = *carry;  // chunk-start state (written by the last segment's lanes one chunk ago)
                 const float4* __restrict__ bq = sB + np * SLOTS + sl * SEGQ;
                 const float4* __restrict__ cq = sC + np * SLOTS + sl * SEGQ;
                 // ---- pass 1: decay factors + local end state ----
@@ -277,9 +279,6 @@ __global__ void __launch_bounds__(32 * WPC, 16 / WPC) scan_fwd_kernel(const Scan
                     Pe = make_float2(1.f, 1.f);
                     He = make_float2(0.f, 0.f);
                 }
-                // ---- chunk-start state (written by the last segment's lanes one chunk ago) ----
-                float2* carry = reinterpret_cast<float2*>(&sCarry[r * npad + n0]);
-                const float2 st = *carry;
                 float2 h = fma2(Pe, st, He);
                 __syncwarp();
                 if (sl == SEGW - 1) *carry = fma2(P2, st, hend);
