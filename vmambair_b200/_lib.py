@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvmambair_b200.so")
+LIB_PATH = os.environ.get("VMB_LIB_PATH") or os.path.join(_HERE, "lib", "libvmambair_b200.so")
 _lib = None
 
 DT_F32, DT_BF16, DT_F16 = 0, 1, 2

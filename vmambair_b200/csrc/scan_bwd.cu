@@ -357,9 +357,10 @@ static int pick_rb_bwd(const ScanBwdParams& p) {
         const int rb = atoi(e);
         if (rb > 0 && rb <= 8 && (rb & (rb - 1)) == 0 && rpg % rb == 0) return rb;
     }
-    int rb = 1;
-    while (rb < 8 && rpg % (rb * 2) == 0) rb *= 2;
-    if (rb == 8 && (long)p.batch * p.dim / 8 < 148L * 4 && rpg % 4 == 0) rb = 4;
+    // few rows -> fewer rows per warp (more warps; their smem footprint still allows >= 3 warps per SM at RB=2)
+    const long rows = (long)p.batch * p.dim;
+    int rb = rows < 1536 ? 2 : rows < 6144 ? 4 : 8;
+    while (rb > 1 && rpg % rb) rb >>= 1;
     return rb;
 }
 

@@ -115,7 +115,10 @@ __device__ __forceinline__ void stage_bc_cta(float4* __restrict__ dst, const in_
     }
 }
 
-template <typename in_t, int RB, int WPC>
+// MODE 0: plain operator, no checkpoints (inference)   1: plain operator + checkpoints (training forward)
+//      2: direction-aware grouped sources (per-group bases, reversed walk), no checkpoints.
+// Each mode only compiles what it needs: the state loop sits at the 128-register limit.
+template <typename in_t, int RB, int WPC, int MODE>
 __global__ void __launch_bounds__(32 * WPC, 16 / WPC) scan_fwd_kernel(const ScanFwdParams p) {
     using Cfg = FwdCfg<RB>;
     using R = FwdRaw<in_t, RB>;
@@ -140,11 +143,12 @@ __global__ void __launch_bounds__(32 * WPC, 16 / WPC) scan_fwd_kernel(const Scan
     const int g = d0 / p.rows_per_group;  // same for every warp of the CTA (RB*WPC divides the group)
     const int N = p.N, L = p.L, npad = p.npad;
     const bool async_ok = p.vec_ok;
+    constexpr bool HAS_REV = MODE == 2;
 
     const in_t *Bg, *Cg, *ublk, *dblk;
     in_t* orow;
     bool rev = false;
-    if (p.ndesc == 0) {
+    if (MODE != 2) {
         Bg = reinterpret_cast<const in_t*>(p.Bm) + (int64_t)b * p.B_bs + (int64_t)g * p.B_gs;
         Cg = reinterpret_cast<const in_t*>(p.Cm) + (int64_t)b * p.C_bs + (int64_t)g * p.C_gs;
         ublk = reinterpret_cast<const in_t*>(p.u) + (int64_t)b * p.u_bs + (int64_t)d0 * p.u_ds;
@@ -158,7 +162,7 @@ __global__ void __launch_bounds__(32 * WPC, 16 / WPC) scan_fwd_kernel(const Scan
         ublk = reinterpret_cast<const in_t*>(gd.u) + (int64_t)b * p.u_bs + (int64_t)dg0 * p.u_ds;
         dblk = reinterpret_cast<const in_t*>(gd.delta) + (int64_t)b * p.dl_bs + (int64_t)dg0 * p.dl_ds;
         orow = reinterpret_cast<in_t*>(gd.out) + (int64_t)b * p.o_bs + (int64_t)(dg0 + r) * p.o_ds;
-        rev = gd.rev != 0;
+        if constexpr (HAS_REV) rev = gd.rev != 0;
     }
     const in_t* __restrict__ urow = ublk + (int64_t)r * p.u_ds;
     const in_t* __restrict__ drow = dblk + (int64_t)r * p.dl_ds;
@@ -185,25 +189,25 @@ __global__ void __launch_bounds__(32 * WPC, 16 / WPC) scan_fwd_kernel(const Scan
         if (async_ok) {
             cp_async_wait_all();
             __syncthreads();  // every copy has landed; every warp is done with the previous B/C tile
-            convert_bc_cta<in_t, RB, NT>(sB, rawBC, tid, rev);
-            convert_bc_cta<in_t, RB, NT>(sC, rawBC + 16 * R::PITCH, tid, rev);
-            if (!rev) {
+            convert_bc_cta<in_t, RB, NT>(sB, rawBC, tid, HAS_REV && rev);
+            convert_bc_cta<in_t, RB, NT>(sC, rawBC + 16 * R::PITCH, tid, HAS_REV && rev);
+            if (!HAS_REV || !rev) {
 #pragma unroll
                 for (int v = 0; v < T / V; ++v) {
                     load_vec_smem<in_t>(raw + r * R::PITCH + sl * T + v * V, uv + v * V);
                     load_vec_smem<in_t>(raw + (RB + r) * R::PITCH + sl * T + v * V, dt + v * V);
                 }
-            } else {  // sequence positions sl*T+t live at raw index CHUNK-1-(sl*T+t)
-                float ur[T], dr[T];
+            } else {  // sequence positions sl*T+t live at raw index CHUNK-1-(sl*T+t): load each vector, place it mirrored
 #pragma unroll
                 for (int v = 0; v < T / V; ++v) {
-                    load_vec_smem<in_t>(raw + r * R::PITCH + CHUNK - (sl + 1) * T + v * V, ur + v * V);
-                    load_vec_smem<in_t>(raw + (RB + r) * R::PITCH + CHUNK - (sl + 1) * T + v * V, dr + v * V);
-                }
+                    float tu[V], td[V];
+                    load_vec_smem<in_t>(raw + r * R::PITCH + CHUNK - (sl + 1) * T + v * V, tu);
+                    load_vec_smem<in_t>(raw + (RB + r) * R::PITCH + CHUNK - (sl + 1) * T + v * V, td);
 #pragma unroll
-                for (int t = 0; t < T; ++t) {
-                    uv[t] = ur[T - 1 - t];
-                    dt[t] = dr[T - 1 - t];
+                    for (int i = 0; i < V; ++i) {
+                        uv[T - 1 - (v * V + i)] = tu[i];
+                        dt[T - 1 - (v * V + i)] = td[i];
+                    }
                 }
             }
             __syncthreads();  // fp32 tile complete, raw buffers free -> refill them while we compute
@@ -246,8 +250,6 @@ __global__ void __launch_bounds__(32 * WPC, 16 / WPC) scan_fwd_kernel(const Scan
             for (int np = 0; np < 8; ++np) {
                 const int n0 = nt * 16 + 2 * np;
                 const float2 A2 = *reinterpret_cast<const float2*>(&sA[r * npad + n0]);
-                float2* carry = reinterpret_cast<float2*>(&sCarry[r * npad + n0]);
-                const float2 st = *carry;  // chunk-start state (written by the last segment's lanes one chunk ago)
                 const float4* __restrict__ bq = sB + np * SLOTS + sl * SEGQ;
                 const float4* __restrict__ cq = sC + np * SLOTS + sl * SEGQ;
                 // ---- pass 1: decay factors + local end state ----
@@ -279,6 +281,8 @@ __global__ void __launch_bounds__(32 * WPC, 16 / WPC) scan_fwd_kernel(const Scan
                     Pe = make_float2(1.f, 1.f);
                     He = make_float2(0.f, 0.f);
                 }
+                float2* carry = reinterpret_cast<float2*>(&sCarry[r * npad + n0]);
+                const float2 st = *carry;  // chunk-start state (written by the last segment's lanes one chunk ago)
                 float2 h = fma2(Pe, st, He);
                 __syncwarp();
                 if (sl == SEGW - 1) *carry = fma2(P2, st, hend);
@@ -292,22 +296,24 @@ __global__ void __launch_bounds__(32 * WPC, 16 / WPC) scan_fwd_kernel(const Scan
                     h = fma2(a2[t + 1], h, mul2(make_float2(dtu[t + 1], dtu[t + 1]), make_float2(Bq.z, Bq.w)));
                     y[t + 1] = fmaf(h.y, Cq.w, fmaf(h.x, Cq.z, y[t + 1]));
                 }
-                if (p.ckpt != nullptr && l0 < L && ((l0 + T) % kScanCkpt) == 0) {
+                if (MODE == 1 && l0 < L && ((l0 + T) % kScanCkpt) == 0) {
                     float* ck = p.ckpt + (((int64_t)b * p.dim + d) * p.n_ckpt + ((l0 + T) / kScanCkpt - 1)) * N + n0;
                     if (n0 < N) ck[0] = h.x;
                     if (n0 + 1 < N) ck[1] = h.y;
                 }
             }
         }
-        if (!rev) {
+        if (!HAS_REV || !rev) {
 #pragma unroll
             for (int v = 0; v < T / V; ++v) store_vec<in_t>(orow + l0 + v * V, y + v * V, valid - v * V, p.vec_ok);
         } else if (valid == T) {  // sequence l0+t -> memory L-1-l0-t: one reversed contiguous block
-            float yr[T];
 #pragma unroll
-            for (int t = 0; t < T; ++t) yr[t] = y[T - 1 - t];
+            for (int v = 0; v < T / V; ++v) {
+                float yr[V];
 #pragma unroll
-            for (int v = 0; v < T / V; ++v) store_vec<in_t>(orow + (L - l0 - T) + v * V, yr + v * V, V, p.vec_ok);
+                for (int i = 0; i < V; ++i) yr[i] = y[T - 1 - (v * V + i)];
+                store_vec<in_t>(orow + (L - l0 - T) + v * V, yr, V, p.vec_ok);
+            }
         } else {
 #pragma unroll
             for (int t = 0; t < T; ++t)
@@ -316,11 +322,11 @@ __global__ void __launch_bounds__(32 * WPC, 16 / WPC) scan_fwd_kernel(const Scan
     }
 }
 
-template <typename in_t, int RB, int WPC>
-static int launch_cfg(const ScanFwdParams& p, cudaStream_t stream) {
+template <typename in_t, int RB, int WPC, int MODE>
+static int launch_cfg2(const ScanFwdParams& p, cudaStream_t stream) {
     using Cfg = FwdCfg<RB>;
     using R = FwdRaw<in_t, RB>;
-    auto kern = scan_fwd_kernel<in_t, RB, WPC>;
+    auto kern = scan_fwd_kernel<in_t, RB, WPC, MODE>;
     const size_t smem = sizeof(float4) * 16 * Cfg::SLOTS + R::bc_bytes + WPC * (R::io_bytes + sizeof(float) * 2 * RB * p.npad);
     VMB_CHECK(smem <= 227 * 1024, "selective_scan_fwd: dstate=%d needs %zu B of shared memory", p.N, smem);
     if (smem > 48 * 1024) VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -328,6 +334,12 @@ static int launch_cfg(const ScanFwdParams& p, cudaStream_t stream) {
     kern<<<(unsigned)blocks, 32 * WPC, smem, stream>>>(p);
     VMB_CUDA(cudaGetLastError());
     return VMB_OK;
+}
+
+template <typename in_t, int RB, int WPC>
+static int launch_cfg(const ScanFwdParams& p, cudaStream_t stream) {
+    if (p.ndesc) return launch_cfg2<in_t, RB, WPC, 2>(p, stream);
+    return p.ckpt ? launch_cfg2<in_t, RB, WPC, 1>(p, stream) : launch_cfg2<in_t, RB, WPC, 0>(p, stream);
 }
 
 // (rows per warp RB, warps per CTA WPC): RB*WPC must divide the rows of a group.  Small RB = more warps and
@@ -343,17 +355,16 @@ static void pick_cfg(const ScanFwdParams& p, int& rb, int& wpc) {
     rb = rows < 1536 ? 1 : rows < 8192 ? 2 : rows < 32768 ? 4 : 8;
     while (rb > 1 && rpg % rb) rb >>= 1;
     // short sequences: a warp-chunk should not be much longer than L
-    while (rb < 32 && rpg % (rb * 2) == 0 && (32 / rb) * T >= 2 * p.L) rb *= 2;
-    if (env_rb > 0 && env_rb <= 32 && (env_rb & (env_rb - 1)) == 0 && rpg % env_rb == 0) rb = env_rb;
+    while (rb < 8 && rpg % (rb * 2) == 0 && (32 / rb) * T >= 2 * p.L) rb *= 2;
+    if (env_rb > 0 && env_rb <= 8 && (env_rb & (env_rb - 1)) == 0 && rpg % env_rb == 0) rb = env_rb;
     wpc = 4;
     while (wpc > 1 && (rpg % (rb * wpc) != 0)) wpc >>= 1;
-    if (env_wpc > 0 && (env_wpc & (env_wpc - 1)) == 0 && rpg % (rb * env_wpc) == 0 && env_wpc <= 8) wpc = env_wpc;
+    if (env_wpc > 0 && (env_wpc & (env_wpc - 1)) == 0 && rpg % (rb * env_wpc) == 0 && env_wpc <= 4) wpc = env_wpc;
 }
 
 template <typename in_t, int RB>
 static int launch_rb(const ScanFwdParams& p, int wpc, cudaStream_t stream) {
     switch (wpc) {
-        case 8: return launch_cfg<in_t, RB, 8>(p, stream);
         case 4: return launch_cfg<in_t, RB, 4>(p, stream);
         case 2: return launch_cfg<in_t, RB, 2>(p, stream);
         default: return launch_cfg<in_t, RB, 1>(p, stream);
@@ -365,8 +376,6 @@ static int launch_t(const ScanFwdParams& p, cudaStream_t stream) {
     int rb, wpc;
     pick_cfg(p, rb, wpc);
     switch (rb) {
-        case 32: return launch_rb<in_t, 32>(p, wpc, stream);
-        case 16: return launch_rb<in_t, 16>(p, wpc, stream);
         case 8: return launch_rb<in_t, 8>(p, wpc, stream);
         case 4: return launch_rb<in_t, 4>(p, wpc, stream);
         case 2: return launch_rb<in_t, 2>(p, wpc, stream);
