@@ -119,7 +119,7 @@ __device__ __forceinline__ void stage_bc_cta(float4* __restrict__ dst, const in_
 //      2: direction-aware grouped sources (per-group bases, reversed walk), no checkpoints.
 // Each mode only compiles what it needs: the state loop sits at the 128-register limit.
 template <typename in_t, int RB, int WPC, int MODE>
-__global__ void __launch_bounds__(32 * WPC, 16 / WPC) scan_fwd_kernel(const ScanFwdParams p) {
+__global__ void __launch_bounds__(32 * WPC, 12 / WPC) scan_fwd_kernel(const ScanFwdParams p) {
     using Cfg = FwdCfg<RB>;
     using R = FwdRaw<in_t, RB>;
     constexpr int SEGW = Cfg::SEGW, CHUNK = Cfg::CHUNK, SEGQ = Cfg::SEGQ, SLOTS = Cfg::SLOTS;
