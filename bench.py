@@ -230,10 +230,15 @@ def run_infer(args):
         "gpu_launches": int(eng.launches_per_step * K),
         "roofline": {"kernel": "scan_fwd_kernel (largest scan of the step: u (8,384,4096) bf16)", "bound": "hbm",
                      "achieved": round(ach, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": round(ach / peak, 4), "traffic": None,
+                     "frac": round(ach / peak, 4),
+                     # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed capture
+                     # profiles/ncu_scan_fwd_r1.txt (46.2 MB + 1.3 MB; below the algorithmic 83.9 MB because the
+                     # operands written by the preceding kernels are still L2-resident)
+                     "traffic": 47.5e6, "traffic_source": "profiles/ncu_scan_fwd_r1.txt (ncu --set full, same command)",
+                     "algorithmic_bytes_per_launch": int(top_b),
                      "all_scans_per_step": {"launches": len(big) // 3, "GB": round(tot_b / 3 / 1e9, 4),
                                             "ms": round(tot_ms / 3, 4), "share_of_step": round(tot_ms / 3 / ms_per_step, 3)},
-                     "note": "selective scan is MUFU(ex2)-bound before HBM at bf16 I/O (SURVEY.md 7.3)"},
+                     "note": "issue/MUFU-bound, not HBM-bound at bf16 I/O (SURVEY.md 7.3): XU pipe 45 %, issue slots 52 % (ncu)"},
         "clocks": clocks,
     }
     if rank == 0:
