@@ -196,9 +196,13 @@ class SS2D_1(nn.Module):
         L = H * W
         x_hwwh = torch.stack([x.flatten(2), x.transpose(2, 3).contiguous().flatten(2)], dim=1)
         xs = torch.cat([x_hwwh, x_hwwh.flip(-1)], dim=1)  # (B,4,C,L): row-major, col-major, and both reversed
-        x_dbl = torch.einsum("bkdl,kcd->bkcl", xs, self.x_proj_weight)
+        # the two per-direction projections as grouped 1x1 conv1d (same contraction as the reference einsums :409-411,
+        # but cuDNN grouped kernels in forward and backward instead of strided batched GEMMs)
+        K, RN = 4, self.dt_rank + 2 * self.d_state
+        x_dbl = F.conv1d(xs.reshape(B, K * C, L), self.x_proj_weight.reshape(K * RN, C, 1), groups=K).view(B, K, RN, L)
         dts, Bs, Cs = torch.split(x_dbl, [self.dt_rank, self.d_state, self.d_state], dim=2)
-        dts = torch.einsum("bkrl,kdr->bkdl", dts, self.dt_projs_weight)
+        dts = F.conv1d(dts.reshape(B, K * self.dt_rank, L), self.dt_projs_weight.reshape(K * C, self.dt_rank, 1),
+                       groups=K).view(B, K, C, L)
         out_y = selective_scan_fn(xs.reshape(B, -1, L), dts.reshape(B, -1, L), -torch.exp(self.A_logs.float()),
                                   Bs.contiguous(), Cs.contiguous(), self.Ds.float(),
                                   delta_bias=self.dt_projs_bias.reshape(-1).float(), delta_softplus=True).view(B, 4, C, L)

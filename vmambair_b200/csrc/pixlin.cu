@@ -10,6 +10,8 @@
 // (the fp32 mode exists for 1e-3 parity against the reference, not for speed).
 // Tile: 64 pixels x 64 output channels per step, the whole K (<=512) of the pixel tile resident in smem so the
 // LayerNorm statistics are computed once in the prologue; larger K streams in chunks of 512.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "oss_params.h"
 
@@ -559,7 +561,8 @@ static int launch2(K kern, PixlinParams p, int PT, cudaStream_t stream) {
 template <typename in_t>
 static int launch_mma(const PixlinParams& p, int out_dtype, cudaStream_t stream) {
     // 128-pixel tiles when there are enough pixels to fill the GPU with them, else 64
-    const bool big = (long)((p.P + 127) / 128) * p.B >= 148 && pixlin_smem(p.K, 2, 128, 2) <= 100 * 1024;
+    bool big = (long)((p.P + 127) / 128) * p.B >= 148 && pixlin_smem(p.K, 2, 128, 2) <= 100 * 1024;
+    if (const char* e = getenv("VMB_PL_PT")) big = big && atoi(e) == 128;  // tuning override
     const int PT = big ? 128 : 64;
     if (out_dtype == VMB_F32)
         return big ? launch2(pixlin_mma_kernel<in_t, float, 128>, p, PT, stream)

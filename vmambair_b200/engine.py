@@ -5,6 +5,8 @@ makes to upscale a batch of LQ tiles (host tensor in, host tensor out).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -30,6 +32,8 @@ class InferenceEngine:
         parallel streams of ONE graph -- images are independent, and most stages of a 64x64 tile are latency-bound
         single-wave launches, so two chains fill the GPU better than one."""
         self.device = torch.device(device)
+        if os.environ.get("VMB_CUDNN_BENCHMARK", "0") == "1":
+            torch.backends.cudnn.benchmark = True  # let cuDNN pick the fastest algorithm for the few non-OSS 3x3 convs (static shapes)
         self.net = cast_for_inference(net.to(self.device).eval(), dtype)
         self.dtype = dtype
         self.x_dev = torch.zeros(batch, in_channels, height, width, device=self.device, dtype=dtype)
