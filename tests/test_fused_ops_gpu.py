@@ -175,3 +175,29 @@ def test_grouped_direction_aware_scan_equals_gathered_scan(dtype, C, H, W):
     torch.testing.assert_close(ys[:, 1].float(), ys_ref[:, 1].float(), rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(ys[:, 2].flip(-1).float(), ys_ref[:, 2].float(), rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(ys[:, 3].flip(-1).float(), ys_ref[:, 3].float(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("K,M,P,B", [(96, 192, 4096, 2), (48, 96, 256, 3), (96, 510, 1024, 2), (256, 96, 512, 1), (288, 768, 64, 4), (384, 96, 64, 2)])
+def test_pixlin_tcgen05_path(dtype, K, M, P, B, monkeypatch):
+    """the tcgen05/TMEM kernel (forced on for every legal shape) against fp32 torch: plain, LN+SiLU range, gate+residual."""
+    from vmambair_b200 import ops
+    monkeypatch.setenv("VMB_PIXLIN_TC", "2")
+    torch.manual_seed(K + M + P)
+    x = (torch.randn(B, K, P, device="cuda") * 1.5 + 0.3).to(dtype)
+    w = ops.pad_weight((torch.randn(M, K, device="cuda") / K ** 0.5).to(dtype))
+    wf = w[:, :K].float()
+    bias = torch.randn(M, device="cuda")
+    out = ops.pixlin(x, w, bias)
+    close(out, torch.einsum("mk,bkp->bmp", wf, x.float()) + bias.view(1, -1, 1), dtype)
+    lw, lb = torch.rand(K, device="cuda") + 0.5, torch.randn(K, device="cuda") * 0.1
+    out = ops.pixlin(x, w, bias, ln=(1, lw, lb), act=(M // 2, M))
+    xn = ln_ref(x.float(), lw, lb).to(dtype).float()
+    ref = torch.einsum("mk,bkp->bmp", wf, xn) + bias.view(1, -1, 1)
+    ref = torch.cat([ref[:, :M // 2], F.silu(ref[:, M // 2:])], 1)
+    close(out, ref, dtype)
+    res = torch.randn(B, M, P, device="cuda").to(dtype)
+    g = torch.randn(B, K, device="cuda") * 0.5
+    out = ops.pixlin(x, w, None, residual=res, gate=g, gate_mode=1)
+    xg = (x.float() * (1 + g[:, :, None])).to(dtype).float()
+    close(out, torch.einsum("mk,bkp->bmp", wf, xg) + res.float(), dtype, scale=4.0)

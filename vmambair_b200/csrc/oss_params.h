@@ -42,6 +42,8 @@ struct ChannelParams {
     int B, C, dc, Rc, N;
 };
 int pixlin_launch(const PixlinParams& p, int dtype, int out_dtype, cudaStream_t stream);
+bool pixlin_tc_applicable(const PixlinParams& p, int dtype, int out_dtype);
+int pixlin_tc_launch(const PixlinParams& p, int dtype, cudaStream_t stream);
 int dwconv_launch(const DwParams& p, int dtype, cudaStream_t stream);
 int cross_scan_launch(const CrossScanParams& p, int dtype, cudaStream_t stream);
 int merge_launch(const MergeParams& p, int dtype, cudaStream_t stream);

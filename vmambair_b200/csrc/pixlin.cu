@@ -588,6 +588,7 @@ int pixlin_launch(const PixlinParams& p, int dtype, int out_dtype, cudaStream_t 
     VMB_CHECK(p.ln_mode == 0 || p.K <= (dtype == VMB_F32 ? PL_KC / 2 : PL2_KC), "pixlin: LayerNorm prologue needs K <= %d",
               dtype == VMB_F32 ? PL_KC / 2 : PL2_KC);
     VMB_CHECK(p.gate_mode == 0 || p.K <= (dtype == VMB_F32 ? PL_KC / 2 : PL2_KC), "pixlin: gate prologue needs resident K");
+    if (pixlin_tc_applicable(p, dtype, out_dtype)) return pixlin_tc_launch(p, dtype, stream);  // tcgen05 / TMEM path
     const size_t smem = pixlin_smem(p.K, dtype == VMB_F32 ? 4 : 2);
     if (dtype == VMB_F32) {
         VMB_CHECK(out_dtype == VMB_F32, "pixlin: fp32 input needs fp32 output");
