@@ -156,7 +156,7 @@ def run_infer(args):
         torch.distributed.init_process_group("nccl", device_id=dev)
     B = B_PER_GPU_INFER
     chains = int(os.environ.get("VMB_CHAINS", "1"))
-    eng = InferenceEngine(build_net("light"), B, H, W, dtype=torch.bfloat16, device=dev, chains=chains)
+    eng = InferenceEngine(build_net(args.net), B, H, W, dtype=torch.bfloat16, device=dev, chains=chains)
     g = torch.Generator().manual_seed(1234 + rank)
     x_host = torch.rand(B, 3, H, W, generator=g).to(torch.bfloat16).pin_memory()
     eng.x_dev.copy_(x_host)
@@ -220,7 +220,8 @@ def run_infer(args):
         "steps": K, "warmup": Wm, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "lq_mpix_per_s": round(value * H * W / 1e6, 3),
-        "config": {"workload": "VmambaIR-light (MambaSISR6 [6,2,2,1]+6, 10.5M params) SRx4 inference, B=8 x 3x64x64 LQ per GPU",
+        "config": {"workload": ("VmambaIR-light (MambaSISR6 [6,2,2,1]+6, 10.5M params)" if args.net == "light" else
+                                "VmambaIR full (MambaSISR6 [15,1,1,1]+15, 12.0M params)") + " SRx4 inference, B=8 x 3x64x64 LQ per GPU",
                    "global_batch": world * B, "parallelism": f"batch-sharded x{world}, no collective",
                    "l2": "256 MiB memset between timed steps", "graph": f"CUDA graph replay, {chains} concurrent sub-batch chains",
                    "path": "fused" if os.environ.get("VMB_PATH", "") != "compose" else "compose"},
@@ -259,6 +260,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="infer", choices=["infer", "train"])
+    ap.add_argument("--net", default="light", choices=["light", "full"],
+                    help="inference net: light = class-default MambaSISR6 [6,2,2,1]+6 (BASELINE configs[1]); full = the YAML's "
+                         "[15,1,1,1]+15 (SURVEY.md 8d asks for both)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

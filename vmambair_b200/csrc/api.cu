@@ -1,3 +1,4 @@
+#include <stdlib.h>
 // C-ABI entry points (include/vmambair_b200.h): argument validation + launch.
 #include <stdarg.h>
 #include <stdio.h>
@@ -7,6 +8,13 @@
 #include "oss_params.h"
 
 namespace vmb {
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("VMB_PDL");
+        return e ? atoi(e) != 0 : true;
+    }();
+    return on;
+}
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
     va_list ap;

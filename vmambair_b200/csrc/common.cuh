@@ -30,6 +30,29 @@ void set_error(const char* fmt, ...);
         }                                                                        \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) ----
+// Every kernel of the library starts with pdl_trigger(); pdl_wait();  -- the next kernel of the stream / graph may become
+// resident while this one drains (its launch latency and whatever it does before its own pdl_wait() overlap our tail);
+// pdl_wait() returns once the preceding kernel has completed and its writes are visible, so nothing that depends on it
+// (and no global store) may precede the wait.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();  // VMB_PDL (default 1), read once
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- scalar conversions ----
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }

@@ -72,6 +72,8 @@ __device__ __forceinline__ void dw_strip(const in_t* __restrict__ xc, const floa
 
 template <typename in_t>
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwParams p) {
+    pdl_trigger();
+    pdl_wait();
     const int c = blockIdx.y % p.Cout, b = blockIdx.y / p.Cout;
     const int L = p.H * p.W;
     const in_t* __restrict__ xb = reinterpret_cast<const in_t*>(p.x) + (int64_t)b * p.x_bs;
@@ -120,9 +122,9 @@ int dwconv_launch(const DwParams& p, int dtype, cudaStream_t stream) {
     const int per_thread = p.vec_ok ? 8 : 1;
     dim3 grid((L / per_thread + 255) / 256 > 0 ? (L / per_thread + 255) / 256 : 1, p.B * p.Cout);
     switch (dtype) {
-        case VMB_F32: dwconv3x3_kernel<float><<<grid, 256, 0, stream>>>(p); break;
-        case VMB_BF16: dwconv3x3_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(p); break;
-        case VMB_F16: dwconv3x3_kernel<__half><<<grid, 256, 0, stream>>>(p); break;
+        case VMB_F32: VMB_CUDA(launch_pdl(dwconv3x3_kernel<float>, grid, dim3(256), 0, stream, p)); break;
+        case VMB_BF16: VMB_CUDA(launch_pdl(dwconv3x3_kernel<__nv_bfloat16>, grid, dim3(256), 0, stream, p)); break;
+        case VMB_F16: VMB_CUDA(launch_pdl(dwconv3x3_kernel<__half>, grid, dim3(256), 0, stream, p)); break;
         default: set_error("dwconv: unsupported dtype %d", dtype); return VMB_ERR_INVALID;
     }
     VMB_CUDA(cudaGetLastError());
@@ -135,6 +137,8 @@ int dwconv_launch(const DwParams& p, int dtype, cudaStream_t stream) {
 
 template <typename in_t>
 __global__ void __launch_bounds__(256) cross_scan_kernel(const CrossScanParams p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float tile[4][32][33];
     const int tiles_w = (p.W + 31) / 32;
     const int th = blockIdx.x / tiles_w, tw = blockIdx.x % tiles_w;
@@ -178,9 +182,9 @@ int cross_scan_launch(const CrossScanParams& p, int dtype, cudaStream_t stream) 
     dim3 grid(((p.H + 31) / 32) * ((p.W + 31) / 32), p.rows, p.B);
     VMB_CHECK(p.rows <= 65535 && p.B <= 65535, "cross_scan: too many rows / batch");
     switch (dtype) {
-        case VMB_F32: cross_scan_kernel<float><<<grid, 256, 0, stream>>>(p); break;
-        case VMB_BF16: cross_scan_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(p); break;
-        case VMB_F16: cross_scan_kernel<__half><<<grid, 256, 0, stream>>>(p); break;
+        case VMB_F32: VMB_CUDA(launch_pdl(cross_scan_kernel<float>, grid, dim3(256), 0, stream, p)); break;
+        case VMB_BF16: VMB_CUDA(launch_pdl(cross_scan_kernel<__nv_bfloat16>, grid, dim3(256), 0, stream, p)); break;
+        case VMB_F16: VMB_CUDA(launch_pdl(cross_scan_kernel<__half>, grid, dim3(256), 0, stream, p)); break;
         default: set_error("cross_scan: unsupported dtype %d", dtype); return VMB_ERR_INVALID;
     }
     VMB_CUDA(cudaGetLastError());
@@ -190,6 +194,8 @@ int cross_scan_launch(const CrossScanParams& p, int dtype, cudaStream_t stream) 
 // ------------------------------------------------------------------------------------------ plane transpose
 template <typename in_t>
 __global__ void __launch_bounds__(256) transpose_hw_kernel(const TransposeParams p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float tile[32][33];
     const int tiles_w = (p.W + 31) / 32;
     const int h0 = (blockIdx.x / tiles_w) * 32, w0 = (blockIdx.x % tiles_w) * 32;
@@ -210,9 +216,9 @@ int transpose_launch(const TransposeParams& p, int dtype, cudaStream_t stream) {
     VMB_CHECK(p.planes <= 65535, "transpose: too many planes");
     dim3 grid(((p.H + 31) / 32) * ((p.W + 31) / 32), p.planes);
     switch (dtype) {
-        case VMB_F32: transpose_hw_kernel<float><<<grid, 256, 0, stream>>>(p); break;
-        case VMB_BF16: transpose_hw_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(p); break;
-        case VMB_F16: transpose_hw_kernel<__half><<<grid, 256, 0, stream>>>(p); break;
+        case VMB_F32: VMB_CUDA(launch_pdl(transpose_hw_kernel<float>, grid, dim3(256), 0, stream, p)); break;
+        case VMB_BF16: VMB_CUDA(launch_pdl(transpose_hw_kernel<__nv_bfloat16>, grid, dim3(256), 0, stream, p)); break;
+        case VMB_F16: VMB_CUDA(launch_pdl(transpose_hw_kernel<__half>, grid, dim3(256), 0, stream, p)); break;
         default: set_error("transpose: unsupported dtype %d", dtype); return VMB_ERR_INVALID;
     }
     VMB_CUDA(cudaGetLastError());
@@ -235,6 +241,8 @@ constexpr int MG_CH = 8;
 
 template <typename in_t>
 __global__ void __launch_bounds__(256) merge_sum_kernel(const MergeParams p, float* __restrict__ msum, float* __restrict__ stats) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sT[2 * MG_CH][16][17];
     const int C = p.C, L = p.H * p.W;
     const int tiles_w = (p.W + 15) / 16;
@@ -286,6 +294,8 @@ __global__ void __launch_bounds__(256) merge_sum_kernel(const MergeParams p, flo
 template <typename in_t>
 __global__ void __launch_bounds__(256) norm_gate_pool_kernel(const MergeParams p, const float* __restrict__ msum,
                                                              const float* __restrict__ stats) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sRed[8];
     const int C = p.C, L = p.H * p.W;
     const int c = blockIdx.x, b = blockIdx.y;
@@ -330,8 +340,8 @@ int merge_launch(const MergeParams& p, int dtype, cudaStream_t stream) {
     VMB_CHECK(gridA.y <= 65535 && p.B <= 65535 && p.C <= 65535, "merge: grid too large");
 #define VMB_MERGE(T)                                                       \
     {                                                                      \
-        merge_sum_kernel<T><<<gridA, 256, 0, stream>>>(p, msum, stats);    \
-        norm_gate_pool_kernel<T><<<gridB, 256, 0, stream>>>(p, msum, stats); \
+        merge_sum_kernel<T><<<gridA, 256, 0, stream>>>(p, msum, stats); /* follows a memset node: plain launch */ \
+        VMB_CUDA(launch_pdl(norm_gate_pool_kernel<T>, gridB, dim3(256), 0, stream, p, (const float*)msum, (const float*)stats)); \
     }
     switch (dtype) {
         case VMB_F32: VMB_MERGE(float) break;
@@ -348,6 +358,7 @@ int merge_launch(const MergeParams& p, int dtype, cudaStream_t stream) {
 // One CTA (256 threads) per image.  Sequence = the C pooled channel means, dc rows, 2 directions, N states.
 
 __global__ void __launch_bounds__(256) channel_branch_kernel(const ChannelParams p) {
+    pdl_trigger();
     extern __shared__ float sm[];
     const int C = p.C, dc = p.dc, Rc = p.Rc, N = p.N, RN = Rc + 2 * N;
     const int CP = C | 1;                // odd row pitch of sDbl: the 16 state lanes of the scan read 16 different rows
@@ -372,6 +383,7 @@ __global__ void __launch_bounds__(256) channel_branch_kernel(const ChannelParams
         sCio[2 * dc + tid] = p.cout_w ? p.cout_w[tid] : 1.f;
     }
     if (tid == 0) sCio[3 * dc] = p.cout_w ? p.cout_b[0] : 0.f;
+    pdl_wait();  // the parameter staging above overlaps the tail of the merge kernels; `pooled` is read from here on
     __syncthreads();
     // xc = conv_cin(pool)  (per-channel affine of the pooled mean)
     for (int i = tid; i < dc * C; i += 256) {
@@ -486,7 +498,7 @@ int channel_launch(const ChannelParams& p, cudaStream_t stream) {
     VMB_CHECK(smem <= 227 * 1024, "channel branch: C=%d too large", p.C);
     if (smem > 48 * 1024)
         VMB_CUDA(cudaFuncSetAttribute(channel_branch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    channel_branch_kernel<<<p.B, 256, smem, stream>>>(p);
+    VMB_CUDA(launch_pdl(channel_branch_kernel, dim3(p.B), dim3(256), smem, stream, p));
     VMB_CUDA(cudaGetLastError());
     return VMB_OK;
 }

@@ -302,6 +302,8 @@ __device__ __forceinline__ void stage_w2(in_t* __restrict__ sW, int WP, const Pi
 
 template <typename in_t, typename out_t, int PT>
 __global__ void __launch_bounds__(PL2_THREADS) pixlin_mma_kernel(const PixlinParams p) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int WN = PT / 4;       // pixels per warp
     constexpr int NT8 = WN / 8;      // n8 tiles per warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -469,6 +471,8 @@ __global__ void __launch_bounds__(PL2_THREADS) pixlin_mma_kernel(const PixlinPar
 // ---- fp32 kernel (FFMA) ----------------------------------------------------------------------------------
 template <typename out_t>
 __global__ void __launch_bounds__(PL_THREADS) pixlin_f32_kernel(const PixlinParams p) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int kpad_all = (p.K + 15) / 16 * 16;
     const int KC = min(kpad_all, PL_KC / 2);
@@ -553,7 +557,7 @@ static int launch2(K kern, PixlinParams p, int PT, cudaStream_t stream) {
     VMB_CHECK(smem <= 227 * 1024, "pixlin: K=%d needs %zu B of shared memory", p.K, smem);
     if (smem > 48 * 1024) VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ptiles, msplit, p.B);
-    kern<<<grid, PL2_THREADS, smem, stream>>>(p);
+    VMB_CUDA(launch_pdl(kern, grid, dim3(PL2_THREADS), smem, stream, p));
     VMB_CUDA(cudaGetLastError());
     return VMB_OK;
 }
@@ -579,7 +583,7 @@ static int launch(K kern, const PixlinParams& p, size_t smem, cudaStream_t strea
     int msplit = 1;
     while (msplit < mtiles && (long)ptiles * p.B * msplit < 148L * 3) ++msplit;
     dim3 grid(ptiles, msplit, p.B);
-    kern<<<grid, PL_THREADS, smem, stream>>>(p);
+    VMB_CUDA(launch_pdl(kern, grid, dim3(PL_THREADS), smem, stream, p));
     VMB_CUDA(cudaGetLastError());
     return VMB_OK;
 }

@@ -214,6 +214,7 @@ template <typename in_t, int KG>
 __global__ void __launch_bounds__(TC_THREADS, 1) pixlin_tc_kernel(const PixlinParams p, const int nacc, const int group,
                                                                   const int tmem_cols, const int wide, const int trace, const int wrep, const int backoff) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    pdl_trigger();  // everything up to pdl_wait() below touches only weights / parameters and this CTA's own state
     long long* tr = (trace && blockIdx.x < 160) ? g_tc_trace + blockIdx.x * 64 : nullptr;
     if (tr && threadIdx.x == 0) tr[0] = gtimer();
     const int kpad = (p.K + 15) / 16 * 16;
@@ -281,6 +282,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pixlin_tc_kernel(const PixlinPa
 
     if (warp == 4) {
         // the first tiles go out before the weights have landed
+        pdl_wait();
         while (issued < my_n && issued < TC_LA) issue_tile(issued++);
     } else {
         // resident weights: every tile of 128 rows, rows >= M zero-filled.  A warp request covers 8 rows x 64 B (whole
@@ -301,6 +303,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pixlin_tc_kernel(const PixlinPa
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        pdl_wait();  // the weight copies fly while the preceding kernel drains; gate / residual / out are touched after this
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&sh->wfull);  // only the MMA warp waits for the weights
@@ -602,7 +605,7 @@ int pixlin_tc_launch(const PixlinParams& p, int dtype, cudaStream_t stream) {
     do {                                                                                               \
         auto k = pixlin_tc_kernel<T, KGV>;                                                             \
         VMB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-        k<<<grid, TC_THREADS, smem, stream>>>(p, nacc, group, cols, wide, trace, wrep, backoff);                             \
+        VMB_CUDA(launch_pdl(k, dim3(grid), dim3(TC_THREADS), smem, stream, p, nacc, group, cols, wide, trace, wrep, backoff));                             \
     } while (0)
     if (dtype == VMB_BF16) {
         if (kg <= 8) VMB_TC_GO(__nv_bfloat16, 8);

@@ -39,6 +39,7 @@ __device__ __forceinline__ void red_add_f32x4(float4* addr, float4 v) {
 
 template <typename in_t, int RB>
 __global__ void __launch_bounds__(32, 8) scan_bwd_kernel(const ScanBwdParams p) {
+    pdl_wait();
     using Cfg = FwdCfg<RB>;
     using R = RawCfg<in_t, RB, 3>;
     constexpr int SEGW = Cfg::SEGW, CHUNK = Cfg::CHUNK, SEGQ = Cfg::SEGQ, SLOTS = Cfg::SLOTS;

@@ -120,6 +120,8 @@ __device__ __forceinline__ void stage_bc_cta(float4* __restrict__ dst, const in_
 // Each mode only compiles what it needs: the state loop sits at the 128-register limit.
 template <typename in_t, int RB, int WPC, int MODE>
 __global__ void __launch_bounds__(32 * WPC, 12 / WPC) scan_fwd_kernel(const ScanFwdParams p) {
+    pdl_trigger();
+    pdl_wait();
     using Cfg = FwdCfg<RB>;
     using R = FwdRaw<in_t, RB>;
     constexpr int SEGW = Cfg::SEGW, CHUNK = Cfg::CHUNK, SEGQ = Cfg::SEGQ, SLOTS = Cfg::SLOTS;
@@ -331,7 +333,7 @@ static int launch_cfg2(const ScanFwdParams& p, cudaStream_t stream) {
     VMB_CHECK(smem <= 227 * 1024, "selective_scan_fwd: dstate=%d needs %zu B of shared memory", p.N, smem);
     if (smem > 48 * 1024) VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long blocks = (long)p.batch * (p.dim / (RB * WPC));
-    kern<<<(unsigned)blocks, 32 * WPC, smem, stream>>>(p);
+    VMB_CUDA(launch_pdl(kern, dim3((unsigned)blocks), dim3(32 * WPC), smem, stream, p));
     VMB_CUDA(cudaGetLastError());
     return VMB_OK;
 }
