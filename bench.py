@@ -156,7 +156,8 @@ def run_infer(args):
         torch.distributed.init_process_group("nccl", device_id=dev)
     B = B_PER_GPU_INFER
     chains = int(os.environ.get("VMB_CHAINS", "1"))
-    eng = InferenceEngine(build_net(args.net), B, H, W, dtype=torch.bfloat16, device=dev, chains=chains)
+    lowres = int(os.environ.get("VMB_LOWRES_CHAINS", "1"))
+    eng = InferenceEngine(build_net(args.net), B, H, W, dtype=torch.bfloat16, device=dev, chains=chains, lowres_chains=lowres)
     g = torch.Generator().manual_seed(1234 + rank)
     x_host = torch.rand(B, 3, H, W, generator=g).to(torch.bfloat16).pin_memory()
     eng.x_dev.copy_(x_host)
@@ -223,7 +224,7 @@ def run_infer(args):
         "config": {"workload": ("VmambaIR-light (MambaSISR6 [6,2,2,1]+6, 10.5M params)" if args.net == "light" else
                                 "VmambaIR full (MambaSISR6 [15,1,1,1]+15, 12.0M params)") + " SRx4 inference, B=8 x 3x64x64 LQ per GPU",
                    "global_batch": world * B, "parallelism": f"batch-sharded x{world}, no collective",
-                   "l2": "256 MiB memset between timed steps", "graph": f"CUDA graph replay, {chains} concurrent sub-batch chains",
+                   "l2": "256 MiB memset between timed steps", "graph": f"CUDA graph replay, {chains} whole-net sub-batch chains, levels below full resolution on {lowres} parallel sub-batch branches",
                    "path": "fused" if os.environ.get("VMB_PATH", "") != "compose" else "compose"},
         "e2e": {"value": round(world * B * K / e2e_s, 2), "unit": "images/s",
                 "h2d_bytes_per_step": int(x_host.numel() * x_host.element_size()),

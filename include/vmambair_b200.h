@@ -145,6 +145,13 @@ int vmb_cross_scan(const vmb_cross_scan_args* a, void* stream);
 typedef struct { const void* x; void* out; int planes, H, W; int dtype; } vmb_transpose_args;
 int vmb_transpose_hw(const vmb_transpose_args* a, void* stream);
 
+/* PixelShuffle(2) of the SR tail (Upsampler, SRGAN/VmambaIR/archs/common.py:45-60; nn.PixelShuffle semantics:
+ * out[b, c, 2h+i, 2w+j] = in[b, 4c + 2i + j, h, w]) on channels-last storage: x (B,H,W,4C) -> out (B,2H,2W,C), so the
+ * 3x3 convs either side run on their native NHWC layout without layout-transform kernels.  A pure permutation:
+ * results are bit-identical to torch.nn.functional.pixel_shuffle. */
+typedef struct { const void* x; void* out; int batch, H, W, C; int dtype; } vmb_pixel_shuffle_args;
+int vmb_pixel_shuffle2_nhwc(const vmb_pixel_shuffle_args* a, void* stream);
+
 /* inverse orders + 4-way fp32 sum (:427-430 / CrossMerge) + out_norm (:433) + gate y*SiLU(z) (:493) +
  * per-(b,c) sums of the result for AdaptiveAvgPool2d (:441; `pooled` fp32 (B,C), fully written).
  * workspace: vmb_merge_workspace_bytes() bytes of device scratch (fp32 merged values + per-pixel statistics). */

@@ -202,3 +202,28 @@ def test_pixlin_tcgen05_path(dtype, K, M, P, B, monkeypatch):
     out = ops.pixlin(x, w, None, residual=res, gate=g, gate_mode=1)
     xg = (x.float() * (1 + g[:, :, None])).to(dtype).float()
     close(out, torch.einsum("mk,bkp->bmp", wf, xg) + res.float(), dtype, scale=4.0)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("B,C,H,W", [(2, 96, 64, 64), (1, 8, 5, 7), (3, 48, 16, 24)])
+def test_pixel_shuffle_nhwc_bit_exact(dtype, B, C, H, W):
+    """the SR tail's PixelShuffle(2) on channels-last storage is the same permutation as F.pixel_shuffle"""
+    from vmambair_b200 import ops
+    torch.manual_seed(B + C + H)
+    x = torch.randn(B, 4 * C, H, W, device="cuda").to(dtype)
+    out = ops.pixel_shuffle2_nhwc(x.contiguous(memory_format=torch.channels_last))
+    ref = F.pixel_shuffle(x, 2)
+    assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(out.contiguous(), ref)
+
+
+def test_sr_tail_channels_last_matches_plain_tail():
+    from vmambair_b200 import archs
+    torch.manual_seed(3)
+    net = archs.MambaSISR6(dim=16, num_blocks=[1, 1, 1, 1], num_refinement_blocks=1).cuda().eval()
+    feat = torch.randn(2, 32, 24, 40, device="cuda")
+    with torch.no_grad():
+        a = net._tail_channels_last(feat)
+        b = net.tail(feat)
+    assert a.shape == b.shape and a.is_contiguous()
+    torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)

@@ -79,6 +79,10 @@ class TransposeArgs(C.Structure):
     _fields_ = [("x", vp), ("out", vp), ("planes", C.c_int), ("H", C.c_int), ("W", C.c_int), ("dtype", C.c_int)]
 
 
+class PixelShuffleArgs(C.Structure):
+    _fields_ = [("x", vp), ("out", vp), ("batch", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("dtype", C.c_int)]
+
+
 class ScanGroupedArgs(C.Structure):
     _fields_ = [
         ("u", vp * 4), ("delta", vp * 4), ("Bm", vp * 4), ("Cm", vp * 4), ("out", vp * 4), ("rev", C.c_int * 4),
@@ -113,6 +117,7 @@ SYMBOLS = {
     "vmb_merge_norm_gate": (C.c_int, [C.POINTER(MergeArgs), vp]),
     "vmb_merge_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "vmb_transpose_hw": (C.c_int, [C.POINTER(TransposeArgs), vp]),
+    "vmb_pixel_shuffle2_nhwc": (C.c_int, [C.POINTER(PixelShuffleArgs), vp]),
     "vmb_selective_scan_fwd_grouped": (C.c_int, [C.POINTER(ScanGroupedArgs), vp]),
     "vmb_channel_branch": (C.c_int, [C.POINTER(ChannelArgs), vp]),
 }

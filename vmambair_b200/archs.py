@@ -345,15 +345,32 @@ class _MamberUNet(nn.Module):
         self.decoder_level1 = stage(dim * 2, num_blocks[0], heads[0])
         self.refinement = stage(dim * 2, num_refinement_blocks, heads[0])
 
-    def _trunk(self, inp_img):
-        e1_in = self.patch_embed(inp_img)
-        e1 = self.encoder_level1(e1_in)
+    _lowres_chains = 1
+    _lowres_streams = ()
+
+    def set_lowres_chains(self, chains: int, streams) -> None:
+        """inference only (vmambair_b200.engine): evaluate the levels below full resolution on `chains` sub-batches in
+        parallel streams -- images are independent, so the result does not change"""
+        self._lowres_chains, self._lowres_streams = int(chains), tuple(streams)
+
+    def _lowres(self, e1):
+        """everything below full resolution: e1 -> up2_1(d2)  (reference forward :612-633)"""
         e2 = self.encoder_level2(self.down1_2(e1))
         e3 = self.encoder_level3(self.down2_3(e2))
         lat = self.latent(self.down3_4(e3))
         d3 = self.decoder_level3(self.reduce_chan_level3(torch.cat([self.up4_3(lat), e3], 1)))
         d2 = self.decoder_level2(self.reduce_chan_level2(torch.cat([self.up3_2(d3), e2], 1)))
-        d1 = self.decoder_level1(torch.cat([self.up2_1(d2), e1], 1))
+        return self.up2_1(d2)
+
+    def _trunk(self, inp_img):
+        e1_in = self.patch_embed(inp_img)
+        e1 = self.encoder_level1(e1_in)
+        if self._lowres_chains > 1 and e1.is_cuda and not torch.is_grad_enabled():
+            from .engine import fork_join_batch
+            up = fork_join_batch(self._lowres, e1, self._lowres_chains, self._lowres_streams)
+        else:
+            up = self._lowres(e1)
+        d1 = self.decoder_level1(torch.cat([up, e1], 1))
         return self.refinement(d1), e1_in
 
 
@@ -369,7 +386,32 @@ class MambaSISR6(_MamberUNet):
 
     def forward(self, inp_img):
         feat, _ = self._trunk(inp_img)
+        if feat.is_cuda and not torch.is_grad_enabled() and feat.dtype in (torch.float32, torch.bfloat16, torch.float16):
+            return self._tail_channels_last(feat) + F.interpolate(inp_img, scale_factor=self.scale, mode="nearest")
         return self.tail(feat) + F.interpolate(inp_img, scale_factor=self.scale, mode="nearest")
+
+    def _tail_channels_last(self, feat):
+        """inference: the SR tail (conv 3x3 -> PixelShuffle(2), twice, conv 3x3; reference common.py:45-60 and
+        MambaSISR6_arch.py:607,640) on NHWC storage end to end -- the convs run on cuDNN's native layout and the pixel
+        shuffles are this library's permutation kernel, instead of an NCHW<->NHWC transform either side of every conv
+        plus an un-vectorised strided copy per shuffle (together ~9 % of the round-1 step).  Same values as self.tail."""
+        from . import ops
+        cache = getattr(self, "_tail_cl", None)
+        ver = tuple((p.data_ptr(), p._version, p.dtype) for p in self.tail.parameters())
+        if cache is None or cache[0] != ver:
+            cache = (ver, {id(m): m.weight.detach().contiguous(memory_format=torch.channels_last)
+                           for m in self.tail.modules() if isinstance(m, nn.Conv2d)})
+            self._tail_cl = cache
+        wcl = cache[1]
+        x = feat.contiguous(memory_format=torch.channels_last)
+        for m in list(self.tail[0]) + [self.tail[1]]:
+            if isinstance(m, nn.Conv2d):
+                x = F.conv2d(x, wcl[id(m)], m.bias, m.stride, m.padding)
+            elif isinstance(m, nn.PixelShuffle) and m.upscale_factor == 2 and x.shape[1] % 8 == 0:
+                x = ops.pixel_shuffle2_nhwc(x.contiguous(memory_format=torch.channels_last))
+            else:
+                x = m(x)
+        return x.contiguous()
 
 
 class MambaRealSR11(MambaSISR6):

@@ -172,6 +172,15 @@ extern "C" int vmb_channel_branch(const vmb_channel_args* a, void* stream) {
     return channel_launch(p, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int vmb_pixel_shuffle2_nhwc(const vmb_pixel_shuffle_args* a, void* stream) {
+    VMB_CHECK(a && a->x && a->out, "pixel_shuffle: null pointer");
+    VMB_CHECK(dt_ok(a->dtype) && a->batch > 0 && a->H > 0 && a->W > 0 && a->C > 0, "pixel_shuffle: bad arguments");
+    VMB_CHECK(aligned16(a->x) && (reinterpret_cast<uintptr_t>(a->out) & 3) == 0, "pixel_shuffle: misaligned pointer");
+    VMB_CHECK((a->C * elt_size(a->dtype)) % 4 == 0, "pixel_shuffle: output pixels must be whole 32-bit words");
+    PixelShuffleParams p{a->x, a->out, a->batch, a->H, a->W, a->C};
+    return pixel_shuffle_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int vmb_transpose_hw(const vmb_transpose_args* a, void* stream) {
     VMB_CHECK(a && a->x && a->out, "transpose: null pointer");
     VMB_CHECK(dt_ok(a->dtype) && a->planes > 0 && a->H > 0 && a->W > 0, "transpose: bad arguments");

@@ -225,6 +225,65 @@ int transpose_launch(const TransposeParams& p, int dtype, cudaStream_t stream) {
     return VMB_OK;
 }
 
+// ------------------------------------------------------------------------------------------ PixelShuffle(2), NHWC
+// One thread moves 16 B of an input pixel's channel vector: 16-bit: channels [8t, 8t+8) = output channels 2t, 2t+1 at the
+// four sub-positions k = 2i + j -> one 32-bit word {c=2t, c=2t+1} to each of the four output pixels (2h+i, 2w+j);
+// fp32: channels [4t, 4t+4) = output channel t at the four sub-positions.  Consecutive threads walk consecutive
+// channels, so both the 16 B loads and the 4 B stores of a warp are contiguous.
+template <typename T>
+__global__ void __launch_bounds__(256) pixel_shuffle2_nhwc_kernel(const PixelShuffleParams p) {
+    pdl_trigger();
+    pdl_wait();
+    constexpr int V = 16 / sizeof(T);        // input channels per thread
+    const int vec_per_px = 4 * p.C / V;
+    const int64_t total = (int64_t)p.B * p.H * p.W * vec_per_px;
+    const uint4* __restrict__ in = reinterpret_cast<const uint4*>(p.x);
+    uint32_t* __restrict__ out = reinterpret_cast<uint32_t*>(p.out);
+    const int words_per_px = p.C * (int)sizeof(T) / 4;  // 32-bit words of one output pixel
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i % vec_per_px);
+        const int64_t px = i / vec_per_px;
+        const int w = (int)(px % p.W);
+        const int64_t bh = px / p.W;
+        const int h = (int)(bh % p.H);
+        const int64_t b = bh / p.H;
+        const uint4 v = __ldg(in + i);
+        uint32_t wk[4];
+        if (sizeof(T) == 2) {
+            // halves e0..e7 of the 16 B: element e = (c - 2t) * 4 + k; word_k = {e_k, e_{4+k}}
+            wk[0] = __byte_perm(v.x, v.z, 0x5410);
+            wk[1] = __byte_perm(v.x, v.z, 0x7632);
+            wk[2] = __byte_perm(v.y, v.w, 0x5410);
+            wk[3] = __byte_perm(v.y, v.w, 0x7632);
+        } else {
+            wk[0] = v.x; wk[1] = v.y; wk[2] = v.z; wk[3] = v.w;
+        }
+        const int64_t row0 = (b * 2 * p.H + 2 * h) * (2 * (int64_t)p.W) + 2 * w;  // output pixel (2h, 2w)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t opx = row0 + (k >> 1) * (2 * (int64_t)p.W) + (k & 1);
+            out[opx * words_per_px + t] = wk[k];
+        }
+    }
+}
+
+int pixel_shuffle_launch(const PixelShuffleParams& p, int dtype, cudaStream_t stream) {
+    const int v = dtype == VMB_F32 ? 4 : 8;
+    VMB_CHECK((4 * p.C) % v == 0, "pixel_shuffle: 4*C must be a multiple of %d", v);
+    const int64_t total = (int64_t)p.B * p.H * p.W * (4 * p.C / v);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    dim3 grid((unsigned)blocks);
+    switch (dtype) {
+        case VMB_F32: VMB_CUDA(launch_pdl(pixel_shuffle2_nhwc_kernel<float>, grid, dim3(256), 0, stream, p)); break;
+        case VMB_BF16: VMB_CUDA(launch_pdl(pixel_shuffle2_nhwc_kernel<__nv_bfloat16>, grid, dim3(256), 0, stream, p)); break;
+        case VMB_F16: VMB_CUDA(launch_pdl(pixel_shuffle2_nhwc_kernel<__half>, grid, dim3(256), 0, stream, p)); break;
+        default: set_error("pixel_shuffle: unsupported dtype %d", dtype); return VMB_ERR_INVALID;
+    }
+    VMB_CUDA(cudaGetLastError());
+    return VMB_OK;
+}
+
 // ------------------------------------------------------------------------------------------ merge + out_norm + gate + pool
 // CTA = (b, 8x8 pixel tile), all C channels.  Phase 1: sum the four directions in the reference's order,
 // (y0 + flip(y2)) + T(y1) + T(flip(y3)), fp32, into smem [C][64].  Phase 2: LayerNorm over C per pixel,

@@ -34,6 +34,10 @@ struct TransposeParams {
     const void* x; void* out;
     int planes, H, W;
 };
+struct PixelShuffleParams {
+    const void* x; void* out;
+    int B, H, W, C;  // C = output channels; the input has 4C
+};
 struct ChannelParams {
     const float* pooled; float inv_count;
     const float* cin_w; const float* cin_b; const float* xc_proj; const float* dtc_w; const float* dtc_b;
@@ -48,6 +52,7 @@ int dwconv_launch(const DwParams& p, int dtype, cudaStream_t stream);
 int cross_scan_launch(const CrossScanParams& p, int dtype, cudaStream_t stream);
 int merge_launch(const MergeParams& p, int dtype, cudaStream_t stream);
 int transpose_launch(const TransposeParams& p, int dtype, cudaStream_t stream);
+int pixel_shuffle_launch(const PixelShuffleParams& p, int dtype, cudaStream_t stream);
 int channel_launch(const ChannelParams& p, cudaStream_t stream);
 }  // namespace vmb
 

@@ -25,12 +25,38 @@ def cast_for_inference(net: torch.nn.Module, dtype: torch.dtype) -> torch.nn.Mod
     return net
 
 
+def fork_join_batch(fn, x: torch.Tensor, chains: int, side_streams) -> torch.Tensor:
+    """fn(x) evaluated on `chains` contiguous sub-batches, sub-batch i > 0 on side_streams[i-1] (forked from / joined
+    back to the current stream with events, so the same code captures into parallel branches of a CUDA graph).
+    Images are independent units of the path, so the result is that of fn(x)."""
+    if chains <= 1 or x.shape[0] % chains != 0:
+        return fn(x)
+    cur = torch.cuda.current_stream(x.device)
+    per = x.shape[0] // chains
+    outs = [None] * chains
+    fork = torch.cuda.Event()
+    fork.record(cur)
+    for i, st in enumerate(side_streams[:chains - 1]):
+        st.wait_event(fork)
+        with torch.cuda.stream(st):
+            outs[i + 1] = fn(x[(i + 1) * per:(i + 2) * per])
+    outs[0] = fn(x[:per])
+    for st in side_streams[:chains - 1]:
+        ev = torch.cuda.Event()
+        ev.record(st)
+        cur.wait_event(ev)
+    return torch.cat(outs, 0)
+
+
 class InferenceEngine:
     def __init__(self, net: torch.nn.Module, batch: int, height: int, width: int, dtype=torch.bfloat16,
-                 device="cuda", in_channels: int = 3, use_graph: bool = True, chains: int = 1):
+                 device="cuda", in_channels: int = 3, use_graph: bool = True, chains: int = 1, lowres_chains: int = 1):
         """chains > 1: the batch is split into `chains` independent sub-batches whose kernel chains are captured on
         parallel streams of ONE graph -- images are independent, and most stages of a 64x64 tile are latency-bound
-        single-wave launches, so two chains fill the GPU better than one."""
+        single-wave launches, so two chains fill the GPU better than one.
+        lowres_chains > 1: only the levels below full resolution (1/2, 1/4, 1/8: 9 of the 27 OSS blocks of the light net,
+        every launch there a fraction of a wave) run as that many parallel sub-batch branches; the full-resolution
+        stages, which fill the GPU on their own, keep the whole batch."""
         self.device = torch.device(device)
         if os.environ.get("VMB_CUDNN_BENCHMARK", "0") == "1":
             torch.backends.cudnn.benchmark = True  # let cuDNN pick the fastest algorithm for the few non-OSS 3x3 convs (static shapes)
@@ -43,6 +69,8 @@ class InferenceEngine:
         self.launches_per_step = 0
         self.chains = chains if (chains > 1 and batch % chains == 0) else 1
         self.side = [torch.cuda.Stream(self.device) for _ in range(self.chains - 1)]
+        if lowres_chains > 1 and hasattr(self.net, "set_lowres_chains"):
+            self.net.set_lowres_chains(lowres_chains, [torch.cuda.Stream(self.device) for _ in range(lowres_chains - 1)])
         with torch.cuda.device(self.device), torch.no_grad():
             with torch.cuda.stream(self.stream):
                 for _ in range(2):  # warm-up (cuDNN autotune, lazy module load) before capture

@@ -205,6 +205,17 @@ def cross_scan(srcs, rows, H, W):
     return out
 
 
+def pixel_shuffle2_nhwc(x):
+    """nn.PixelShuffle(2) on a channels-last tensor: x logical (B,4C,H,W) with NHWC storage -> (B,C,2H,2W), NHWC storage.
+    Bit-identical to F.pixel_shuffle(x, 2)."""
+    B, C4, H, W = x.shape
+    assert C4 % 4 == 0 and x.is_contiguous(memory_format=torch.channels_last)
+    out = torch.empty((B, C4 // 4, 2 * H, 2 * W), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    a = _lib.PixelShuffleArgs(_ptr(x), _ptr(out), B, H, W, C4 // 4, _DT[x.dtype])
+    _run("vmb_pixel_shuffle2_nhwc", a, x, "pixel_shuffle")
+    return out
+
+
 def transpose_hw(x, H, W):
     """x: (B, C, H*W) contiguous -> (B, C, W*H) with every plane transposed."""
     assert x.is_contiguous()
