@@ -227,3 +227,21 @@ def test_sr_tail_channels_last_matches_plain_tail():
         b = net.tail(feat)
     assert a.shape == b.shape and a.is_contiguous()
     torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("variant,dim", [("sisr", 96), ("mamber33", 48), ("realsr", 64), ("mamber32", 40)])
+def test_channel_branch_versions_agree(variant, dim, monkeypatch):
+    """the channel-direction OSS: restructured kernel (v2, default) against the first version, all model variants"""
+    from vmambair_b200 import archs, fused, ops
+    torch.manual_seed(dim)
+    blk = archs.MamberBlock(dim=dim, num_heads=1, ffn_expansion_factor=2.66, bias=False, LayerNorm_type="WithBias", variant=variant).cuda()
+    with torch.no_grad():
+        for p_ in blk.parameters():
+            p_.add_(0.05 * torch.randn_like(p_))
+    c = fused._prepare(blk, torch.float32, torch.device("cuda"))
+    pooled = torch.randn(5, dim, device="cuda") * 40.0
+    monkeypatch.setenv("VMB_CH_V", "1")
+    v1 = ops.channel_branch(pooled, 1.0 / 64, c["ch"], dim)
+    monkeypatch.setenv("VMB_CH_V", "2")
+    v2 = ops.channel_branch(pooled, 1.0 / 64, c["ch"], dim)
+    torch.testing.assert_close(v2, v1, rtol=1e-4, atol=1e-5)

@@ -9,6 +9,8 @@
 //   channel_branch_kernel  the whole channel OSS (cforward_corev1 :438-483 and the 3 other variants) for one
 //                          image in one CTA: conv_cin, xc_proj, dtc_proj, bidirectional scan over L=C,
 //                          conv_cout, channel_norm -> c[b][C]
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "oss_params.h"
 
@@ -549,11 +551,183 @@ __global__ void __launch_bounds__(256) channel_branch_kernel(const ChannelParams
     for (int l = tid; l < C; l += 256) p.c_out[(int64_t)b * C + l] = (sOut[l] - mu) * rstd * p.cn_w[l] + p.cn_b[l];
 }
 
+// Second version (default): 512 threads, row-per-warp loops without integer division, and a scan whose serial loop
+// carries only the h recurrence -- exp / dt*u*B are independent of h and are hoisted eight positions ahead, the
+// per-position sum over the 16 states (a 4-stage shuffle chain per position in v1) becomes a store of h*C into
+// shared memory and one parallel reduction afterwards.
+// debug trace (VMB_CH_TRACE=1): %globaltimer of CTA 0 after each phase
+__device__ long long g_ch_trace[16];
+__device__ __forceinline__ long long ch_gtimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr int CH2_THREADS = 512;
+
+__global__ void __launch_bounds__(CH2_THREADS) channel_branch_v2_kernel(const ChannelParams p, const int trace) {
+    pdl_trigger();
+    extern __shared__ float sm[];
+    const int C = p.C, dc = p.dc, Rc = p.Rc, N = p.N, RN = Rc + 2 * N;
+    const int CP = C | 1;                 // odd row pitch: the 16 state lanes touch 16 different rows without bank conflicts
+    const int rows = 2 * dc;              // (direction, row) scan rows
+    float* sSeq = sm;                     // [dc][C]     xc
+    float* sDbl = sSeq + dc * C;          // [2][RN][CP] xc_dbl per direction (direction order)
+    float* sDt = sDbl + 2 * RN * CP;      // [2][dc][C]  softplus'ed dt
+    float* sY = sDt + rows * C;           // [2][dc][C]  scan outputs (direction order)
+    float* sOut = sY + rows * C;          // [C]
+    float* sRed = sOut + C;               // [64]
+    float* sXp = sRed + 64;               // [2][RN][dc]
+    float* sDw = sXp + 2 * RN * dc;       // [2][dc][Rc]
+    float* sDb = sDw + 2 * dc * Rc;       // [2][dc]
+    float* sCio = sDb + 2 * dc;           // cin_w[dc] cin_b[dc] cout_w[dc] cout_b[1]
+    float* sHC = sCio + 3 * dc + 1;       // [rows][16][CP]  h * C per state
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = CH2_THREADS / 32;
+    long long* tr = (trace && b == 0 && tid == 0) ? g_ch_trace : nullptr;
+    if (tr) tr[0] = ch_gtimer();
+    for (int i = tid; i < 2 * RN * dc; i += CH2_THREADS) sXp[i] = p.xc_proj[i];
+    for (int i = tid; i < 2 * dc * Rc; i += CH2_THREADS) sDw[i] = p.dtc_w[i];
+    if (tid < 2 * dc) sDb[tid] = p.dtc_b[tid];
+    if (tid < dc) {
+        sCio[tid] = p.cin_w ? p.cin_w[tid] : 1.f;
+        sCio[dc + tid] = p.cin_w ? p.cin_b[tid] : 0.f;
+        sCio[2 * dc + tid] = p.cout_w ? p.cout_w[tid] : 1.f;
+    }
+    if (tid == 0) sCio[3 * dc] = p.cout_w ? p.cout_b[0] : 0.f;
+    // scan parameters of this thread's (row, state): weights, loaded ahead of the wait
+    const int srow = tid >> 4, n = tid & 15;
+    const bool sact = srow < rows && n < N;
+    const float A2 = sact ? -__expf(p.Ac_logs[srow * N + n]) * kLog2e : 0.f;
+    pdl_wait();  // the parameter staging above overlaps the tail of the merge kernels; `pooled` is read from here on
+    __syncthreads();
+    if (tr) tr[1] = ch_gtimer();
+    // xc = conv_cin(pool)  (per-channel affine of the pooled mean): warp j-strided rows, lanes over the sequence
+    for (int j = warp; j < dc; j += NW)
+        for (int l = lane; l < C; l += 32) sSeq[j * C + l] = fmaf(p.pooled[(int64_t)b * C + l] * p.inv_count, sCio[j], sCio[dc + j]);
+    __syncthreads();
+    if (tr) tr[2] = ch_gtimer();
+    // xc_dbl[k][c][l] = sum_j W[k][c][j] * xs[k][j][l],  xs[1] = flipped sequence
+    for (int kc = warp; kc < 2 * RN; kc += NW) {
+        const int k = kc >= RN;
+        const float* wrow = sXp + kc * dc;
+        for (int l = lane; l < C; l += 32) {
+            const int ls = k ? C - 1 - l : l;
+            float a = 0.f;
+            for (int j = 0; j < dc; ++j) a = fmaf(wrow[j], sSeq[j * C + ls], a);
+            sDbl[kc * CP + l] = a;
+        }
+    }
+    __syncthreads();
+    if (tr) tr[3] = ch_gtimer();
+    // dt[k][j][l] = softplus(sum_r Wdt[k][j][r] * dbl[k][r][l] + bias)
+    for (int kj = warp; kj < rows; kj += NW) {
+        const int k = kj / dc;
+        for (int l = lane; l < C; l += 32) {
+            float a = sDb[kj];
+            for (int r = 0; r < Rc; ++r) a = fmaf(sDw[kj * Rc + r], sDbl[(k * RN + r) * CP + l], a);
+            sDt[kj * C + l] = softplus_f(a);
+        }
+    }
+    __syncthreads();
+    if (tr) tr[4] = ch_gtimer();
+    // sequential scan: thread = (row, state n)
+    if (srow < rows) {
+        const int k = srow / dc, j = srow - k * dc;
+        const float* __restrict__ dtr = sDt + srow * C;
+        const float* __restrict__ ur = sSeq + j * C;
+        const float* __restrict__ Br = sDbl + (k * RN + Rc + (sact ? n : 0)) * CP;
+        const float* __restrict__ Cr = sDbl + (k * RN + Rc + N + (sact ? n : 0)) * CP;
+        float* __restrict__ hc = sHC + (srow * 16 + n) * CP;
+        float h = 0.f;
+        int l = 0;
+        for (; l + 8 <= C; l += 8) {
+            float a[8], bu[8], cv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float dt = dtr[l + i];
+                const float u = ur[k ? C - 1 - (l + i) : l + i];
+                a[i] = ex2(dt * A2);
+                bu[i] = sact ? dt * u * Br[l + i] : 0.f;
+                cv[i] = sact ? Cr[l + i] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                h = fmaf(a[i], h, bu[i]);
+                hc[l + i] = h * cv[i];
+            }
+        }
+        for (; l < C; ++l) {
+            const float dt = dtr[l];
+            const float u = ur[k ? C - 1 - l : l];
+            h = fmaf(ex2(dt * A2), h, sact ? dt * u * Br[l] : 0.f);
+            hc[l] = sact ? h * Cr[l] : 0.f;
+        }
+    }
+    __syncthreads();
+    if (tr) tr[5] = ch_gtimer();
+    // y[row][l] = D u + sum over the 16 state slots
+    for (int row = warp; row < rows; row += NW) {
+        const int k = row / dc, j = row - k * dc;
+        const float Dv = p.Dsc[row];
+        for (int l = lane; l < C; l += 32) {
+            float y = 0.f;
+#pragma unroll
+            for (int s = 0; s < 16; ++s) y += sHC[(row * 16 + s) * CP + l];
+            sY[row * C + l] = fmaf(Dv, sSeq[j * C + (k ? C - 1 - l : l)], y);
+        }
+    }
+    __syncthreads();
+    if (tr) tr[6] = ch_gtimer();
+    // merge directions, conv_cout, channel_norm over the C positions
+    float part = 0.f;
+    for (int l = tid; l < C; l += CH2_THREADS) {
+        float acc = sCio[3 * dc];
+        for (int j = 0; j < dc; ++j) {
+            const float y = sY[(0 * dc + j) * C + l] + sY[(1 * dc + j) * C + (C - 1 - l)];
+            acc = fmaf(y, sCio[2 * dc + j], acc);
+        }
+        sOut[l] = acc;
+        part += acc;
+    }
+    auto block_sum = [&](float v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if (lane == 0) sRed[warp] = v;
+        __syncthreads();
+        float t = 0.f;
+        for (int i = 0; i < NW; ++i) t += sRed[i];
+        return t;
+    };
+    const float mu = block_sum(part) / C;
+    float vp = 0.f;
+    for (int l = tid; l < C; l += CH2_THREADS) {
+        const float d = sOut[l] - mu;
+        vp += d * d;
+    }
+    const float rstd = rsqrtf(block_sum(vp) / C + 1e-5f);
+    for (int l = tid; l < C; l += CH2_THREADS) p.c_out[(int64_t)b * C + l] = (sOut[l] - mu) * rstd * p.cn_w[l] + p.cn_b[l];
+    if (tr) tr[7] = ch_gtimer();
+}
+
 int channel_launch(const ChannelParams& p, cudaStream_t stream) {
     VMB_CHECK(p.N <= 16, "channel branch: dstate <= 16 supported (got %d)", p.N);
     const int RN = p.Rc + 2 * p.N;
-    const size_t smem = sizeof(float) * ((size_t)p.dc * p.C + 2 * RN * (p.C | 1) + 4 * p.dc * p.C + p.C + 64 + 2 * RN * p.dc +
+    const size_t base = sizeof(float) * ((size_t)p.dc * p.C + 2 * RN * (p.C | 1) + 4 * p.dc * p.C + p.C + 64 + 2 * RN * p.dc +
                                          2 * p.dc * p.Rc + 2 * p.dc + 3 * p.dc + 1);
+    const char* ve = getenv("VMB_CH_V");
+    const int version = ve ? atoi(ve) : 2;
+    const size_t smem2 = base + sizeof(float) * (size_t)2 * p.dc * 16 * (p.C | 1);
+    if (version == 2 && 2 * p.dc * 16 <= CH2_THREADS && smem2 <= 227 * 1024) {
+        const char* te = getenv("VMB_CH_TRACE");
+        const int trace = te ? atoi(te) : 0;
+        if (smem2 > 48 * 1024)
+            VMB_CUDA(cudaFuncSetAttribute(channel_branch_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        VMB_CUDA(launch_pdl(channel_branch_v2_kernel, dim3(p.B), dim3(CH2_THREADS), smem2, stream, p, trace));
+        VMB_CUDA(cudaGetLastError());
+        return VMB_OK;
+    }
+    const size_t smem = base;
     VMB_CHECK(smem <= 227 * 1024, "channel branch: C=%d too large", p.C);
     if (smem > 48 * 1024)
         VMB_CUDA(cudaFuncSetAttribute(channel_branch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -563,3 +737,8 @@ int channel_launch(const ChannelParams& p, cudaStream_t stream) {
 }
 
 }  // namespace vmb
+
+// debug only (not part of the public header): phase stamps of CTA 0 of the last traced channel-branch launch
+extern "C" int vmb_debug_ch_trace(long long* dst, int n) {
+    return cudaMemcpyFromSymbol(dst, vmb::g_ch_trace, sizeof(long long) * (size_t)n) == cudaSuccess ? 0 : 1;
+}
