@@ -245,3 +245,23 @@ def test_channel_branch_versions_agree(variant, dim, monkeypatch):
     monkeypatch.setenv("VMB_CH_V", "2")
     v2 = ops.channel_branch(pooled, 1.0 / 64, c["ch"], dim)
     torch.testing.assert_close(v2, v1, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("H,W", [(64, 64), (8, 8), (16, 32), (32, 16), (4, 256)])
+def test_dwconv_row_block_kernel_bit_identical(dtype, H, W, monkeypatch):
+    """the 4-row / shuffle-halo kernel (default for power-of-two planes) against the strip kernel: same fmaf order"""
+    from vmambair_b200 import ops
+    torch.manual_seed(H + W)
+    B, C = 3, 7
+    x = torch.randn(B, 2 * C + 3, H, W, device="cuda").to(dtype)  # channel-offset view: x_cs != H*W rows of a larger tensor
+    xin = x.view(B, 2 * C + 3, H * W)[:, 1:2 * C + 1]
+    w = (torch.randn(2 * C, 9, device="cuda") * 0.3).contiguous()
+    b = torch.randn(2 * C, device="cuda") * 0.1
+    outs = {}
+    for v in ("1", "2"):
+        monkeypatch.setenv("VMB_DW_V", v)
+        outs[v] = (ops.dwconv3x3(xin[:, :C], w[:C].contiguous(), b[:C].contiguous(), C, H, W, 0),
+                   ops.dwconv3x3(xin, w, b, C, H, W, 1), ops.dwconv3x3(xin, w, None, C, H, W, 1))
+    for a, r in zip(outs["2"], outs["1"]):
+        assert torch.equal(a, r)

@@ -119,8 +119,119 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwParams p) {
     }
 }
 
+// Row-block version (W a power of two in [8, 256], H % 4 == 0, 16 B aligned rows): one thread = an 8-pixel strip of FOUR
+// consecutive output rows, so six 16 B row loads feed four outputs (v1: three loads per output), and the left / right halo
+// pixels come from the neighbouring lanes' vectors by shuffle instead of two scalar loads per row.  Same fmaf order as v1
+// (dy ascending, dx ascending; out-of-image taps contribute fmaf(k, 0, acc) = acc), so the results are bit-identical.
+template <typename in_t>
+__device__ __forceinline__ void dw_rows4(const in_t* __restrict__ xc, const float* __restrict__ w9, int h0, int w0, int s, int S,
+                                         int H, int W, float bias, float (*acc)[8]) {
+    constexpr int V = Vec<in_t>::N;
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[o][i] = bias;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        const int hh = h0 - 1 + r;
+        float v[10];
+        if (hh >= 0 && hh < H) {
+            const in_t* __restrict__ row = xc + (int64_t)hh * W + w0;
+#pragma unroll
+            for (int j = 0; j < 8 / V; ++j) load_vec<in_t>(row + j * V, v + 1 + j * V, V, true);
+        } else {
+#pragma unroll
+            for (int i = 1; i <= 8; ++i) v[i] = 0.f;
+        }
+        const float left = __shfl_up_sync(0xffffffffu, v[8], 1, S), right = __shfl_down_sync(0xffffffffu, v[1], 1, S);
+        v[0] = s > 0 ? left : 0.f;
+        v[9] = s < S - 1 ? right : 0.f;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const int dy = r - 1 - o;  // input row r feeds output row o with tap row dy
+            if (dy >= -1 && dy <= 1) {
+                const float k0 = w9[(dy + 1) * 3], k1 = w9[(dy + 1) * 3 + 1], k2 = w9[(dy + 1) * 3 + 2];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[o][i] = fmaf(k2, v[i + 2], fmaf(k1, v[i + 1], fmaf(k0, v[i], acc[o][i])));
+            }
+        }
+    }
+}
+
+template <typename in_t>
+__global__ void __launch_bounds__(256) dwconv3x3_rows4_kernel(const DwParams p, const int S, const int log2_tpp, const long total) {
+    pdl_trigger();
+    pdl_wait();
+    constexpr int V = Vec<in_t>::N;
+    const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = gt < total;
+    const long g = valid ? gt : total - 1;      // clamped: every lane takes part in the shuffles
+    const int plane = (int)(g >> log2_tpp), t = (int)(g & ((1L << log2_tpp) - 1));
+    const int c = plane % p.Cout, b = plane / p.Cout;
+    const int s = t & (S - 1), h0 = (t / S) * 4, w0 = s * 8;
+    const in_t* __restrict__ xb = reinterpret_cast<const in_t*>(p.x) + (int64_t)b * p.x_bs;
+    in_t* __restrict__ ob = reinterpret_cast<in_t*>(p.out) + (int64_t)b * p.o_bs + (int64_t)c * p.o_cs;
+    float w0k[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) w0k[i] = p.w[c * 9 + i];
+    float a0[4][8];
+    dw_rows4<in_t>(xb + (int64_t)c * p.x_cs, w0k, h0, w0, s, S, p.H, p.W, p.bias ? p.bias[c] : 0.f, a0);
+    if (p.mode == 0) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a0[o][i] = silu2(a0[o][i]);
+    } else {
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a0[o][i] = gelu_exact(a0[o][i]);
+        float w1k[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) w1k[i] = p.w[(c + p.Cout) * 9 + i];
+        float a1[4][8];
+        dw_rows4<in_t>(xb + (int64_t)(c + p.Cout) * p.x_cs, w1k, h0, w0, s, S, p.H, p.W, p.bias ? p.bias[c + p.Cout] : 0.f, a1);
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a0[o][i] *= a1[o][i];
+    }
+    if (!valid) return;
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int j = 0; j < 8 / V; ++j) store_vec<in_t>(ob + (int64_t)(h0 + o) * p.W + w0 + j * V, a0[o] + j * V, V, true);
+}
+
+template <typename in_t>
+static int dwconv_rows4_launch(const DwParams& p, cudaStream_t stream) {
+    const int S = p.W / 8;
+    const long tpp = (long)S * (p.H / 4);
+    int lg = 0;
+    while ((1L << lg) < tpp) ++lg;
+    const long total = tpp * p.B * p.Cout;
+    VMB_CUDA(launch_pdl(dwconv3x3_rows4_kernel<in_t>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, p, S, lg, total));
+    VMB_CUDA(cudaGetLastError());
+    return VMB_OK;
+}
+
 int dwconv_launch(const DwParams& p, int dtype, cudaStream_t stream) {
     const int L = p.H * p.W;
+    {
+        const char* ve = getenv("VMB_DW_V");
+        const int version = ve ? atoi(ve) : 2;
+        const int S = p.W / 8;
+        const long tpp = (long)S * (p.H / 4);
+        // W and the threads per plane powers of two (plane index by shift, halo shuffles inside one row of strips)
+        if (version == 2 && p.vec_ok && p.W >= 8 && p.W <= 256 && (p.W & (p.W - 1)) == 0 && p.H % 4 == 0 && (tpp & (tpp - 1)) == 0) {
+            switch (dtype) {
+                case VMB_F32: return dwconv_rows4_launch<float>(p, stream);
+                case VMB_BF16: return dwconv_rows4_launch<__nv_bfloat16>(p, stream);
+                case VMB_F16: return dwconv_rows4_launch<__half>(p, stream);
+                default: set_error("dwconv: unsupported dtype %d", dtype); return VMB_ERR_INVALID;
+            }
+        }
+    }
     const int per_thread = p.vec_ok ? 8 : 1;
     dim3 grid((L / per_thread + 255) / 256 > 0 ? (L / per_thread + 255) / 256 : 1, p.B * p.Cout);
     switch (dtype) {
