@@ -568,12 +568,15 @@ bool pixlin_tc_applicable(const PixlinParams& p, int dtype, int out_dtype) {
                        p.M <= TC_MAXMT * TC_MT && p.K <= 8 * TC_KGMAX && tc_smem_bytes(p) <= TC_SMEM_MAX;
     if (!legal || mode == 2) return legal;
     // round-1 measurements (tools/pixlin_bench.py, profiles/pixlin_tc_r1.md): the fixed cost of a launch (barriers, TMEM,
-    // ~5-9 us for the resident weights) needs >= 4 tiles per SM to amortise, and the single-warp-per-column LayerNorm /
-    // gate prologue paces the pipeline at ~2 us per tile, so the pipeline wins for wide outputs (>= 3 weight tiles) and
-    // for deep reductions without a prologue; everything else stays on the mma.sync kernel
+    // ~5-9 us for the resident weights, partly hidden behind the previous kernel by the programmatic launch) needs >= 4
+    // tiles per SM to amortise, and the LayerNorm / gate prologue warps pace the pipeline at ~2 us per tile at K = 96.
+    // Measured wins at B=8, 64x64: no prologue with K > 128 or M > 128 (x_proj fold, project_out of C=96), LayerNorm with
+    // M > 256 (project_in, C=96) or with K <= 64 and M > 128 (project_in, C=48); everything else stays on mma.sync
     const long tiles = (long)(p.P / TC_PT) * p.B;
     const bool has_pro = p.ln_mode != 0 || p.gate_mode != 0;
-    return tiles >= 4L * tc_num_sms() && (p.M > 2 * TC_MT || (!has_pro && p.K > 128));
+    if (tiles < 4L * tc_num_sms()) return false;
+    if (!has_pro) return p.K > 128 || p.M > 128;
+    return p.gate_mode == 0 && (p.M > 2 * TC_MT || (p.K <= 64 && p.M > TC_MT));
 }
 
 int pixlin_tc_launch(const PixlinParams& p, int dtype, cudaStream_t stream) {
