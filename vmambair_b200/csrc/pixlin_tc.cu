@@ -4,14 +4,15 @@
 // 32-pixel tiles of the (b, p) plane:
 //   warp 4   producer : cp.async of the next activation tiles into a 6-stage ring (MN-major canonical layout: pixels are
 //                       the contiguous dimension of NCHW), 4 tiles in flight, mbarrier "full" per stage
-//   warp 6   prologue : LayerNorm / channel gate on the resident tile, in place (only when the call has one)
+//   warps 6-9 prologue: LayerNorm / channel gate on the resident tile, in place, one 8-pixel column group per warp
+//                       (only when the call has one)
 //   warp 5   MMA      : one lane issues ceil(M/128) x K/16 tcgen05.mma (128 x 32 x 16) per tile into one of up to four
 //                       TMEM accumulator stages and commits to the "stage empty" / "accumulator full" mbarriers
 //   warps 0-3 epilogue: tcgen05.ld of their 32 TMEM lanes (lane = output channel = one contiguous pixel row),
 //                       bias / SiLU / residual, 32 B vector stores (STG.256)
 // so loads, tensor-core math and stores of different tiles overlap, and the weights are read once per SM instead of
-// once per tile.  Used for 16-bit I/O with 16 B aligned rows, M <= 512 and weights + ring <= 227 KB (everything the
-// OSS block needs at full resolution); the mma.sync kernel in pixlin.cu covers ragged / small problems, FFMA fp32.
+// once per tile.  Legal for 16-bit I/O with 16 B aligned rows, M <= 512, K <= 256 and weights + ring <= 227 KB; used where
+// measured faster than the mma.sync kernel of pixlin.cu (pixlin_tc_applicable below); FFMA kernel for fp32.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -28,7 +29,6 @@ constexpr int TC_THREADS = 320;  // 4 epilogue warps + producer + MMA + 4 prolog
 constexpr int TC_KGMAX = 32;     // K <= 256: a prologue lane keeps its column of the tile in registers
 constexpr int TC_MAXMT = 4;      // M <= 512
 constexpr int TC_NACC = 4;       // TMEM accumulator stages (nmt*32 columns each)
-constexpr int TC_NACC4 = 4;
 constexpr size_t TC_SMEM_MAX = 227 * 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -211,8 +211,8 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 
 // KG: compile-time bound on K/8 (a prologue lane keeps that many packed pixel pairs in registers)
 template <typename in_t, int KG>
-__global__ void __launch_bounds__(TC_THREADS, 1) pixlin_tc_kernel(const PixlinParams p, const int nacc, const int group,
-                                                                  const int tmem_cols, const int wide, const int trace, const int wrep, const int backoff) {
+__global__ void __launch_bounds__(TC_THREADS, 1) pixlin_tc_kernel(const PixlinParams p, const int tmem_cols, const int wide,
+                                                                  const int trace, const int backoff) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     pdl_trigger();  // everything up to pdl_wait() below touches only weights / parameters and this CTA's own state
     long long* tr = (trace && blockIdx.x < 160) ? g_tc_trace + blockIdx.x * 64 : nullptr;
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pixlin_tc_kernel(const PixlinPa
     const int my_n = ((int)blockIdx.x < total) ? (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const bool has_pro = p.ln_mode != 0 || p.gate_mode != 0;
     const in_t* __restrict__ xg = reinterpret_cast<const in_t*>(p.x);
-    const in_t* __restrict__ w = reinterpret_cast<const in_t*>(p.w) + (size_t)(wrep > 1 ? blockIdx.x % wrep : 0) * p.M * p.w_ld;
+    const in_t* __restrict__ w = reinterpret_cast<const in_t*>(p.w);
 
     // ---- setup: barriers, TMEM, LayerNorm parameters ----
     if (tid == 0) {
@@ -432,9 +432,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pixlin_tc_kernel(const PixlinPa
         mbar_wait(&sh->wfull, 0);
         if (tr && lane == 0) tr[2] = gtimer();
         for (int it = 0; it < my_n; ++it) {
-            const int s = it % TC_NS, a = it % TC_NACC4;
+            const int s = it % TC_NS, a = it % TC_NACC;
             mbar_wait(has_pro ? &sh->ready[s] : &sh->full[s], (it / TC_NS) & 1);
-            mbar_wait(&sh->acce[a], ((it / TC_NACC4) & 1) ^ 1);
+            mbar_wait(&sh->acce[a], ((it / TC_NACC) & 1) ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (tr && lane == 0 && it < 10) tr[4 + 6 * it + 2] = gtimer();
             const uint64_t bd0 = x_desc0 + (uint64_t)((s * x_stage) >> 4);
@@ -462,10 +462,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pixlin_tc_kernel(const PixlinPa
         const in_t* __restrict__ resg = reinterpret_cast<const in_t*>(p.residual);
         in_t* __restrict__ og = reinterpret_cast<in_t*>(p.out);
         for (int it = 0; it < my_n; ++it) {
-            const int a = it % TC_NACC4;
+            const int a = it % TC_NACC;
             const int t = blockIdx.x + it * gridDim.x;
             const int b = t / ptiles, p0 = (t - b * ptiles) * TC_PT;
-            mbar_wait_sleep(&sh->accf[a], (it / TC_NACC4) & 1, backoff);
+            mbar_wait_sleep(&sh->accf[a], (it / TC_NACC) & 1, backoff);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (tr && tid == 0 && it < 10) tr[4 + 6 * it + 4] = gtimer();
             const uint32_t t_acc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * nmt * TC_PT);
@@ -582,14 +582,9 @@ bool pixlin_tc_applicable(const PixlinParams& p, int dtype, int out_dtype) {
 int pixlin_tc_launch(const PixlinParams& p, int dtype, cudaStream_t stream) {
     const size_t smem = tc_smem_bytes(p);
     const int nmt = (p.M + TC_MT - 1) / TC_MT;
-    // accumulator stages of nmt*32 TMEM columns each (<= 512 columns); the MMA warp interleaves `group` tiles so that
-    // group*nmt >= 4 independent accumulators are in flight, and two groups fit in TMEM (MMA overlaps the epilogue)
-    int group = 1, nacc = 4;  // (interleaving accumulators was measured slower: the MMA is bound by the smem read of A)
-    if (const char* e = getenv("VMB_TC_GROUP")) {
-        group = atoi(e);
-        nacc = group > 2 ? 8 : 4;
-        if (nacc * nmt * TC_PT > 512) { group = 1; nacc = 4; }
-    }
+    // TC_NACC accumulator stages of nmt*32 TMEM columns each (<= 512 columns).  (Interleaving the MMAs of several tiles /
+    // weight tiles over independent accumulators was measured slower, see profiles/pixlin_tc_r1.md.)
+    const int nacc = TC_NACC;
     int cols = 32;
     while (cols < nacc * nmt * TC_PT) cols <<= 1;
     const long total = (long)(p.P / TC_PT) * p.B;
@@ -597,8 +592,6 @@ int pixlin_tc_launch(const PixlinParams& p, int dtype, cudaStream_t stream) {
     auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
     const char* be = getenv("VMB_TC_BACKOFF");
     const int backoff = be ? atoi(be) : 100;
-    const char* we = getenv("VMB_TC_WREP");  // debug experiment: the caller laid out this many copies of W back to back
-    const int wrep = we ? atoi(we) : 1;
     const char* te = getenv("VMB_TC_TRACE");
     const int trace = te ? atoi(te) : 0;
     const int wide = al32(p.out) && p.o_bs % 16 == 0 && p.o_cs % 16 == 0 &&
@@ -608,7 +601,7 @@ int pixlin_tc_launch(const PixlinParams& p, int dtype, cudaStream_t stream) {
     do {                                                                                               \
         auto k = pixlin_tc_kernel<T, KGV>;                                                             \
         VMB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-        VMB_CUDA(launch_pdl(k, dim3(grid), dim3(TC_THREADS), smem, stream, p, nacc, group, cols, wide, trace, wrep, backoff));                             \
+        VMB_CUDA(launch_pdl(k, dim3(grid), dim3(TC_THREADS), smem, stream, p, cols, wide, trace, backoff));                             \
     } while (0)
     if (dtype == VMB_BF16) {
         if (kg <= 8) VMB_TC_GO(__nv_bfloat16, 8);
