@@ -107,6 +107,22 @@ def test_lowres_parallel_branches_do_not_change_the_result():
     assert (y1 - y2).abs().max() < 0.03 and (y1 - y4).abs().max() < 0.03 and (y1 - y2).abs().mean() < 2e-3
 
 
+@pytest.mark.parametrize("cls,size,batch", [("Mamber32", 256, 1), ("MambaRealSR11", 128, 2)])
+def test_large_tiles_fused_path_matches_composed_path(cls, size, batch):
+    """BASELINE configs 4 / 5 geometry (deraining 256x256: L = 65 536 at level 1; RealSR 128x128: L = 16 384) through the
+    fused inference pipeline against the composed torch + scan-operator path of the same module, fp32"""
+    torch.manual_seed(4)
+    kw = dict(num_blocks=[1, 1, 1, 1], num_refinement_blocks=1)
+    net = getattr(archs, cls)(**kw).cuda().eval()
+    x = torch.rand(batch, 3, size, size, device="cuda")
+    with torch.no_grad():
+        y_fused = net(x)
+    with torch.enable_grad():
+        y_comp = net(x).detach()
+    assert y_fused.shape == y_comp.shape
+    torch.testing.assert_close(y_fused, y_comp, rtol=2e-3, atol=2e-4)
+
+
 def test_unmodified_call_pattern_selective_scan_cuda_core():
     """The B0 boundary: fwd/bwd with the reference binding's signature and return order."""
     import vmambair_b200.selective_scan_cuda_core as core

@@ -19,7 +19,7 @@ namespace vmb {
 
 constexpr int PL_PT = 64;      // pixels per CTA
 constexpr int PL_MT = 64;      // output channels per step
-constexpr int PL_KC = 512;     // resident K chunk
+constexpr int PL_KC = 768;     // resident K chunk: PL_KC / 2 = 384 fp32 rows (the widest LayerNorm of the nets, dim*8; 221 KB of smem)
 constexpr int PL_THREADS = 128;
 
 template <typename T> struct MmaType;
