@@ -1,10 +1,12 @@
 """Fused inference pipeline of one OSS block: 15 launches of this library's kernels instead of the ~85
 un-fused PyTorch ops of the reference MamberBlock.forward (SRGAN/VmambaIR/archs/MambaSISR6_arch.py:486-515).
 
-   norm1+in_conv(+SiLU z) -> dwconv3x3+SiLU -> x_proj (+dt_proj folded: W_dt W_x is a CxC map, so the four
-   directions' delta, B, C come out of ONE GEMM on the un-permuted x) -> 4-direction index gather ->
-   selective scan -> inverse gather + 4-way sum + out_norm + gate + pooling -> channel-direction OSS (1 CTA/image)
-   -> channel gate + out_conv + residual -> norm2+project_in -> dwconv3x3 + GELU gate -> project_out + residual
+   norm1+in_conv(+SiLU z) -> dwconv3x3+SiLU -> transpose (the (W,H) copy of x) -> x_proj (+dt_proj folded: W_dt W_x is a
+   CxC map, so delta, B, C of directions 0/2 come out of ONE GEMM on x and of 1/3 out of one GEMM on x^T) ->
+   direction-aware selective scan (reversal inside the kernel, no gathered operands) -> 4-way sum in the reference's
+   order + out_norm + gate + pooling -> channel-direction OSS (1 CTA/image) -> channel gate + out_conv + residual ->
+   norm2+project_in -> dwconv3x3 + GELU gate -> project_out + residual
+   (shapes with L % 8 != 0 take the explicit cross_scan gather instead of the direction-aware scan)
 
 No CPU path, no silent fallback: every stage goes through the C-ABI and raises on failure.
 """
