@@ -91,26 +91,50 @@ def build_net(kind):
     return archs.MambaSISR6(num_blocks=[15, 1, 1, 1], num_refinement_blocks=15)  # options/MambaSISR15_x4.yml
 
 
-def cpu_oracle_images_per_s(steps, warmup, threads=None):
-    """The reference path on the host CPU: oracle port (oracle/oss_ref.py + C scan), one image per step."""
+METRIC = "SRx4 images/sec (64x64 LQ, bf16)"  # BASELINE.json's metric; both arms print this exact string
+
+
+def workload_name(net):
+    return ("VmambaIR-light (MambaSISR6 [6,2,2,1]+6, 10.5M params)" if net == "light" else
+            "VmambaIR full (MambaSISR6 [15,1,1,1]+15, 12.0M params)") + " SRx4 inference, B=8 x 3x64x64 LQ per GPU"
+
+
+def host_threads():
+    """CPU threads this process may use: the scheduler affinity mask (respects cgroup cpusets / taskset), not os.cpu_count()."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def bench_input(rank=0):
+    """the synthetic LQ batch of the bench (B_PER_GPU_INFER x 3 x 64 x 64 in [0,1]); image 0 of rank 0 is the CPU sample"""
+    g = torch.Generator().manual_seed(1234 + rank)
+    return torch.rand(B_PER_GPU_INFER, 3, H, W, generator=g)
+
+
+def cpu_oracle_images_per_s(steps, warmup, threads=None, x=None, kind="light"):
+    """The reference path on the host CPU: oracle port (oracle/oss_ref.py + C scan), one image per step.
+    -> (images/s, mean seconds, output of the last forward)"""
     from oracle import oss_ref, cscan
     cscan.build()
-    threads = threads or os.cpu_count() // 2 or 1  # physical cores; torchrun would otherwise pin OMP_NUM_THREADS=1
+    threads = threads or host_threads()  # torchrun would otherwise pin OMP_NUM_THREADS=1
     torch.set_num_threads(threads)
     cscan.set_threads(threads)
-    net = build_net("light")
+    net = build_net(kind)
     sd = {k: v.detach().float() for k, v in net.state_dict().items()}
-    g = torch.Generator().manual_seed(1)
-    x = torch.rand(1, 3, H, W, generator=g)
+    if x is None:
+        x = bench_input(0)[:1]
     ts = []
+    y = None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         with torch.no_grad():
-            oss_ref.net_forward(sd, x, "sisr")
+            y = oss_ref.net_forward(sd, x.float(), "sisr")
         if i >= warmup:
             ts.append(time.perf_counter() - t0)
     mean = sum(ts) / len(ts)
-    return 1.0 / mean, mean
+    return 1.0 / mean, mean, y
 
 
 def run_reference(args):
@@ -118,15 +142,16 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count()
-    ips, mean = cpu_oracle_images_per_s(args.steps, args.warmup)
+    ips, mean, _ = cpu_oracle_images_per_s(args.steps, args.warmup, kind=args.net)
     out = {
-        "impl": "reference", "metric": "SRx4 images/sec (64x64 LQ)", "value": round(ips, 4), "unit": "images/s",
+        "impl": "reference", "metric": METRIC, "value": round(ips, 4), "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(mean * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "VmambaIR-light (MambaSISR6 [6,2,2,1]+6) SRx4 inference, 3x64x64 LQ",
-                   "sample": "1 image per step through the CPU oracle port of the reference path"},
+        "config": {"workload": workload_name(args.net),
+                   "sample": "bounded sample: 1 image of the batch per step through the CPU oracle port of the reference path"},
         "cpu_baseline": {"value": round(ips, 4), "unit": "images/s", "cores": torch.get_num_threads(), "host_cores": cores,
-                         "kind": "port", "sample": "full VmambaIR-light forward of one 3x64x64 image per step (fp32, oracle/oss_ref.py + OpenMP C scan)"},
+                         "affinity_cores": host_threads(),
+                         "kind": "port", "sample": "full VmambaIR-light forward of one 3x64x64 image per step (fp32 arithmetic: the reference has no bf16 CPU path; oracle/oss_ref.py + OpenMP C scan)"},
         "e2e": {"value": round(ips, 4), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -158,8 +183,7 @@ def run_infer(args):
     chains = int(os.environ.get("VMB_CHAINS", "1"))
     lowres = int(os.environ.get("VMB_LOWRES_CHAINS", "1"))
     eng = InferenceEngine(build_net(args.net), B, H, W, dtype=torch.bfloat16, device=dev, chains=chains, lowres_chains=lowres)
-    g = torch.Generator().manual_seed(1234 + rank)
-    x_host = torch.rand(B, 3, H, W, generator=g).to(torch.bfloat16).pin_memory()
+    x_host = bench_input(rank).to(torch.bfloat16).pin_memory()
     eng.x_dev.copy_(x_host)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     K, Wm = args.steps, max(args.warmup, 3)
@@ -197,7 +221,10 @@ def run_infer(args):
     clocks = sampler.stop() if rank == 0 else None
     # ---- roofline of the dominant kernel (selective scan fwd): per-launch CUDA events over eager steps ----
     rec = []
-    eager = InferenceEngine(eng.net, B, H, W, dtype=torch.bfloat16, device=dev, use_graph=False)
+    y_bench = eng.run(x_host).float().clone()  # result of the benchmarked engine: sanity / parity check below
+    if not bool(torch.isfinite(y_bench).all()):
+        raise SystemExit("bench.py: the benchmarked forward produced non-finite values")
+    eager = InferenceEngine(build_net(args.net), B, H, W, dtype=torch.bfloat16, device=dev, use_graph=False)
     eager.x_dev.copy_(x_host)
     eager.step_device()
     torch.cuda.synchronize(dev)
@@ -217,15 +244,14 @@ def run_infer(args):
     ms_per_step = total_ms / K
     value = world * B * K / (total_ms * 1e-3)
     out = {
-        "metric": "SRx4 images/sec (64x64 LQ, bf16)", "value": round(value, 2), "unit": "images/s", "n_gpus": world,
+        "metric": METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": world,
         "steps": K, "warmup": Wm, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "lq_mpix_per_s": round(value * H * W / 1e6, 3),
-        "config": {"workload": ("VmambaIR-light (MambaSISR6 [6,2,2,1]+6, 10.5M params)" if args.net == "light" else
-                                "VmambaIR full (MambaSISR6 [15,1,1,1]+15, 12.0M params)") + " SRx4 inference, B=8 x 3x64x64 LQ per GPU",
+        "config": {"workload": workload_name(args.net),
                    "global_batch": world * B, "parallelism": f"batch-sharded x{world}, no collective",
                    "l2": "256 MiB memset between timed steps", "graph": f"CUDA graph replay, {chains} whole-net sub-batch chains, levels below full resolution on {lowres} parallel sub-batch branches",
-                   "path": "fused" if os.environ.get("VMB_PATH", "") != "compose" else "compose"},
+                   "path": f"fused OSS kernels ({eng.launches_per_step} launches of this library per step)" if eng.launches_per_step else "compose"},
         "e2e": {"value": round(world * B * K / e2e_s, 2), "unit": "images/s",
                 "h2d_bytes_per_step": int(x_host.numel() * x_host.element_size()),
                 "d2h_bytes_per_step": int(y.numel() * y.element_size())},
@@ -233,10 +259,8 @@ def run_infer(args):
         "roofline": {"kernel": "scan_fwd_kernel (largest scan of the step: u (8,384,4096) bf16)", "bound": "hbm",
                      "achieved": round(ach, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": round(ach / peak, 4),
-                     # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed capture
-                     # profiles/ncu_scan_fwd_r1.txt (46.2 MB + 1.3 MB; below the algorithmic 83.9 MB because the
-                     # operands written by the preceding kernels are still L2-resident)
-                     "traffic": 47.5e6, "traffic_source": "profiles/ncu_scan_fwd_r1.txt (ncu --set full, same command)",
+                     # dram__bytes_* of this launch are not measurable outside ncu: null here, the committed capture is cited
+                     "traffic": None, "traffic_cited": "profiles/ncu_scan_fwd_r2.txt (ncu --set full of this kernel inside this command)",
                      "algorithmic_bytes_per_launch": int(top_b),
                      "all_scans_per_step": {"launches": len(big) // 3, "GB": round(tot_b / 3 / 1e9, 4),
                                             "ms": round(tot_ms / 3, 4), "share_of_step": round(tot_ms / 3 / ms_per_step, 3)},
@@ -245,10 +269,16 @@ def run_infer(args):
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            ips, mean = cpu_oracle_images_per_s(steps=2, warmup=1)
+            ips, mean, y_ref = cpu_oracle_images_per_s(steps=2, warmup=1, x=x_host[:1], kind=args.net)
             out["cpu_baseline"] = {"value": round(ips, 4), "unit": "images/s", "cores": torch.get_num_threads(),
                                    "host_cores": os.cpu_count(), "kind": "port",
-                                   "sample": f"2 timed forwards of one 3x64x64 image, fp32 CPU oracle port ({mean:.2f} s each)"}
+                                   "sample": f"2 timed forwards of image 0 of the bench batch (3x64x64), fp32 CPU oracle port ({mean:.2f} s each)"}
+            # the benchmarked bf16 result against the fp32 oracle on the same image (bound of tests/test_bench_parity_gpu.py)
+            err = (y_bench[:1].cpu() - y_ref).abs()
+            out["parity"] = {"vs": "oracle/oss_ref.net_forward (fp32) on image 0", "max_abs_err": round(float(err.max()), 5),
+                             "mean_abs_err": round(float(err.mean()), 6), "bound": {"max": 0.1, "mean": 0.01}}
+            if float(err.max()) > 0.1 or float(err.mean()) > 0.01:
+                raise SystemExit(f"bench.py: benchmarked output off the oracle: {out['parity']}")
         print(json.dumps(out), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

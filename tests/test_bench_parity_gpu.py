@@ -1,0 +1,185 @@
+"""GPU parity on the BENCHMARKED configurations (BASELINE.json configs[1], [3], [4]) against the CPU module oracle,
+and of the scan operator against the reference's own CUDA kernel (oracle/_ref, rebuilt for sm_100a from the
+sources under /root/reference by oracle/build_ref.py) on identical inputs.
+
+Tolerances
+  * fp32 whole-network vs oracle/oss_ref.net_forward: rtol 1e-3 / atol 1e-4 (the module bar of the block goldens);
+  * bf16 whole-network (bf16 weights + activations, fp32 scan state) vs the fp32 oracle: max |err| <= 0.1 and
+    mean |err| <= 0.01 on outputs in [0, 1] + O(1) residual -- bf16 has 8 significant bits (2^-8 = 3.9e-3 per
+    rounding), the network is 27 blocks deep;
+  * scan vs the reference CUDA kernel: the reference test's own tolerances (test_selective_scan.py:398-400, 490-502).
+"""
+import importlib.util
+import os
+
+import pytest
+import torch
+
+import vmambair_b200.archs as archs
+from oracle import cscan, oss_ref
+
+pytestmark = pytest.mark.gpu
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "selective_scan_cuda_core.so")
+
+
+def _oracle(net, x, kind):
+    cscan.set_threads(len(os.sched_getaffinity(0)))
+    sd = {k: v.detach().float().cpu().clone() for k, v in net.state_dict().items()}
+    with torch.no_grad():
+        return oss_ref.net_forward(sd, x.float().cpu(), kind)
+
+
+def _bf16_bound(y, ref):
+    err = (y.float().cpu() - ref).abs()
+    assert torch.isfinite(y).all()
+    assert err.max() <= 0.1 and err.mean() <= 0.01, (float(err.max()), float(err.mean()))
+
+
+# ----------------------------------------------------------------------------- BASELINE configs[1]: the bench net
+def _bench_net_and_input():
+    torch.manual_seed(0)
+    net = archs.MambaSISR6().eval()  # "VmambaIR-light": class default [6,2,2,1]+6 (bench.py build_net("light"))
+    x = torch.rand(8, 3, 64, 64, generator=torch.Generator().manual_seed(1234))
+    return net, x
+
+
+def test_bench_net_fp32_fused_vs_oracle():
+    net, x = _bench_net_and_input()
+    ref = _oracle(net, x, "sisr")
+    net = net.cuda()
+    with torch.no_grad():
+        y = net(x.cuda())
+    torch.testing.assert_close(y.cpu(), ref, rtol=1e-3, atol=1e-4)
+
+
+def test_bench_net_bf16_engine_vs_oracle():
+    from vmambair_b200.engine import InferenceEngine
+    net, x = _bench_net_and_input()
+    ref = _oracle(net, x.to(torch.bfloat16), "sisr")  # same bf16-rounded input, fp32 arithmetic
+    eng = InferenceEngine(net, 8, 64, 64, dtype=torch.bfloat16)
+    y = eng.run(x.to(torch.bfloat16)).clone()
+    _bf16_bound(y, ref)
+
+
+# ----------------------------------------------------------------------------- configs[3] / [4] geometry vs the oracle
+@pytest.mark.parametrize("cls,kind,size,batch", [("Mamber32", "mamber32", 256, 1), ("MambaRealSR11", "realsr", 128, 2)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_config45_geometry_vs_oracle(cls, kind, size, batch, dtype):
+    """deraining 256x256 (L = 65 536 at level 1) and RealSR 128x128 (L = 16 384), one block per stage, fused path vs the
+    CPU oracle (not vs forward_compose)."""
+    torch.manual_seed(4)
+    net = getattr(archs, cls)(num_blocks=[1, 1, 1, 1], num_refinement_blocks=1).eval()
+    x = torch.rand(batch, 3, size, size, generator=torch.Generator().manual_seed(7))
+    if dtype == torch.float32:
+        ref = _oracle(net, x, kind)
+        with torch.no_grad():
+            y = net.cuda()(x.cuda())
+        torch.testing.assert_close(y.cpu(), ref, rtol=1e-3, atol=1e-4)
+    else:
+        from vmambair_b200.engine import InferenceEngine
+        ref = _oracle(net, x.to(dtype), kind)
+        eng = InferenceEngine(net, batch, size, size, dtype=dtype, use_graph=False)
+        _bf16_bound(eng.run(x.to(dtype)).clone(), ref)
+
+
+# ----------------------------------------------------------------------------- scan vs the reference CUDA kernel
+def _ref_ext():
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref/selective_scan_cuda_core.so not built (needs /root/reference at build time)")
+    spec = importlib.util.spec_from_file_location("selective_scan_cuda_core", REF_SO)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def _ref_inputs(b, dim, L, itype, G=4, N=16):
+    """distributions and seed of the reference test (test_selective_scan.py:406-441)"""
+    torch.random.manual_seed(0)
+    dev = "cuda"
+    A = -0.5 * torch.rand(dim, N, device=dev)
+    Bm = torch.randn(b, G, N, L, device=dev, dtype=itype)
+    Cm = torch.randn(b, G, N, L, device=dev, dtype=itype)
+    D = torch.randn(dim, device=dev)
+    bias = 0.5 * torch.rand(dim, device=dev)
+    u = torch.randn(b, dim, L, device=dev, dtype=itype)
+    delta = 0.5 * torch.rand(b, dim, L, device=dev, dtype=itype)
+    return u, delta, A, Bm, Cm, D, bias
+
+
+def _ref_tol(itype):
+    rtol, atol = (6e-4, 2e-3) if itype == torch.float32 else (3e-3, 5e-3)
+    if itype == torch.bfloat16:
+        rtol, atol = 3e-2, 5e-2
+    return rtol, atol, 1e-3, 1e-3
+
+
+@pytest.mark.parametrize("b", [8, 4, 1])
+@pytest.mark.parametrize("itype", [torch.float32, torch.bfloat16])
+def test_scan_fwd_bwd_vs_reference_cuda_kernel(b, itype):
+    """u (b, 4*96, 4096): the north-star shape at the bench (8), training (4) and single-image (1) batch, against
+    selective_scan_cuda_core.fwd / .bwd of the reference itself on the same tensors."""
+    import vmambair_b200.selective_scan_cuda_core as ours
+    ref = _ref_ext()
+    args = _ref_inputs(b, 384, 4096, itype)
+    rtol, atol, rtolw, atolw = _ref_tol(itype)
+    out_r, x_r = ref.fwd(*args, True, 1)
+    out_o, x_o = ours.fwd(*args, True, 1)
+    assert torch.allclose(out_o, out_r, rtol=rtol, atol=atol), float((out_o.float() - out_r.float()).abs().max())
+    g = torch.randn_like(out_r)
+    gr = ref.bwd(*args, g, x_r, True, 1)
+    go = ours.bwd(*args, g, x_o, True, 1)
+    names = ("du", "ddelta", "dA", "dB", "dC", "dD", "ddelta_bias")
+    # (rtol, atol) per output as in the reference test :490-502; the fp32 accumulators dA/dD/dbias sum b*L = 4k..32k terms in a
+    # different order in the two kernels (both use float atomics), so their bound scales with the magnitude of the result
+    tols = [(rtol * 2, atol * 2), (rtol * 5, atol * 10), (rtolw, atolw * 5), (rtol, atol), (rtol, atol), (rtolw, atolw), (rtolw, atolw)]
+    for n, a, r, (rt, at) in zip(names, go, gr, tols):
+        a, r = a.float(), r.float()
+        assert a.shape == r.shape, n
+        if n in ("dA", "dD", "ddelta_bias"):
+            at = at + 1e-3 * float(r.abs().max())
+        bad = (a - r).abs() > at + rt * r.abs()
+        assert not bad.any(), f"{n}: {int(bad.sum())}/{bad.numel()} out of tolerance, max err {float((a - r).abs().max()):.3e}, max |ref| {float(r.abs().max()):.3e}"
+
+
+def test_b0_boundary_values_match_oracle():
+    """selective_scan_cuda_core.fwd/.bwd shim: values, not only shapes, against the sequential oracle."""
+    import vmambair_b200.selective_scan_cuda_core as core
+    torch.manual_seed(0)
+    u = torch.randn(2, 8, 70); dl = torch.rand(2, 8, 70)
+    A = -torch.rand(8, 16); Bm = torch.randn(2, 2, 16, 70); Cm = torch.randn(2, 2, 16, 70)
+    D = torch.randn(8); bias = torch.rand(8); dout = torch.randn(2, 8, 70)
+    cu = [t.cuda() for t in (u, dl, A, Bm, Cm, D, bias)]
+    out, x = core.fwd(*cu, True, 1)
+    ref = cscan.scan_fwd(u, dl, A, Bm, Cm, D, bias, True, fp64=True)
+    torch.testing.assert_close(out.double().cpu(), ref, rtol=1e-3, atol=1e-5)
+    grads = core.bwd(*cu, dout.cuda(), x, True, 1)
+    refg = cscan.scan_bwd(u, dl, A, Bm, Cm, D, bias, dout, True)
+    assert len(grads) == 7
+    for n, a, r in zip(("du", "ddelta", "dA", "dB", "dC", "dD", "dbias"), grads, refg):
+        torch.testing.assert_close(a.double().cpu(), r, rtol=2e-3, atol=2e-4, msg=lambda m, n=n: f"{n}: {m}")
+
+
+@pytest.mark.parametrize("itype", [torch.float32, torch.bfloat16])
+def test_bwd_north_star_shape_vs_oracle(itype):
+    """backward at (1, 384, 4096) -- reference-test distribution, element-wise bound (reference test :490-502 pattern:
+    rtol/atol scaled per output) against the analytic fp64 oracle."""
+    from vmambair_b200 import ops
+    args = [t.cpu() for t in _ref_inputs(1, 384, 4096, itype)]
+    dout = torch.randn(1, 384, 4096, generator=torch.Generator().manual_seed(3)).to(itype)
+    cu = [t.cuda() for t in args]
+    out, ck = ops.selective_scan_fwd(*cu, True, True)
+    grads = ops.selective_scan_bwd(*cu, dout.cuda(), ck, True)
+    refg = cscan.scan_bwd(*args, dout, True)
+    rtol, atol, rtolw, atolw = _ref_tol(itype)
+    tols = [(rtol * 2, atol * 2), (rtol * 5, atol * 10), (rtolw, atolw * 5), (rtol, atol), (rtol, atol), (rtolw, atolw), (rtolw, atolw)]
+    for n, a, r, (rt, at) in zip(("du", "ddelta", "dA", "dB", "dC", "dD", "dbias"), grads, refg, tols):
+        a, r = a.double().cpu(), r.double()
+        if n in ("dA", "dD", "dbias"):
+            at = at + 1e-3 * float(r.abs().max())
+        bad = (a - r).abs() > at + rt * r.abs()
+        assert not bad.any(), f"{n}: {int(bad.sum())}/{bad.numel()} out of tolerance, max err {float((a - r).abs().max()):.3e}"

@@ -14,8 +14,8 @@ Reference classes mirrored (file:line in /root/reference):
   Upsampler / default_conv (SR tail)                     SRGAN/VmambaIR/archs/common.py:7-8,45-60
 
 Two execution paths share the parameters:
-  * `fused`  (default on CUDA, inference & training): the hand-written kernels (vmambair_b200.fused) --
-    there is no silent fallback: if the CUDA library is missing a RuntimeError is raised;
+  * `fused`  (CUDA, no-grad calls): the hand-written kernels (vmambair_b200.fused) -- if the CUDA library is missing a
+    RuntimeError is raised; shapes outside the kernels' limits (fused.unsupported_reason) take `compose` with a warning;
   * `compose`: the same math composed from torch ops + this repo's selective-scan operator with autograd
     (used for training until every fused stage has its backward, and as the module-level cross-check).
 """
@@ -80,7 +80,7 @@ class LayerNorm(nn.Module):
     def forward(self, x):
         b, c, h, w = x.shape
         y = self.body(x.flatten(2).transpose(1, 2))
-        return y.transpose(1, 2).reshape(b, c, h, w)
+        return y.transpose(1, 2).reshape(b, c, h, w).to(x.dtype)
 
 
 # ----------------------------------------------------------------------------- EFFN

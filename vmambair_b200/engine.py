@@ -5,6 +5,7 @@ makes to upscale a batch of LQ tiles (host tensor in, host tensor out).
 """
 from __future__ import annotations
 
+import copy
 import os
 
 import torch
@@ -17,11 +18,17 @@ _FP32_PARAMS = ("A_logs", "Ac_logs", "Ds", "Dsc", "dt_projs_bias", "dtc_projs_bi
 
 
 def cast_for_inference(net: torch.nn.Module, dtype: torch.dtype) -> torch.nn.Module:
+    """In-place cast of `net` (callers that keep training the same module pass a copy: InferenceEngine deep-copies).
+    Parameters the fused kernels consume in fp32 (LayerNorm affine, conv biases, scan parameters) keep an un-rounded fp32
+    master in `p._vmb_master`, so a bf16 engine does not round them twice."""
     for name, p in net.named_parameters():
         if name.rsplit(".", 1)[-1] in _FP32_PARAMS:
             p.data = p.data.float()
         else:
+            master = p.data.float() if (p.dim() == 1 and dtype != torch.float32) else None
             p.data = p.data.to(dtype)
+            if master is not None:
+                p._vmb_master = master
     return net
 
 
@@ -60,7 +67,8 @@ class InferenceEngine:
         self.device = torch.device(device)
         if os.environ.get("VMB_CUDNN_BENCHMARK", "0") == "1":
             torch.backends.cudnn.benchmark = True  # let cuDNN pick the fastest algorithm for the few non-OSS 3x3 convs (static shapes)
-        self.net = cast_for_inference(net.to(self.device).eval(), dtype)
+        # the caller's module is left untouched (it may be the training replica): the engine owns a cast copy
+        self.net = cast_for_inference(copy.deepcopy(net).to(self.device).eval(), dtype)
         self.dtype = dtype
         self.x_dev = torch.zeros(batch, in_channels, height, width, device=self.device, dtype=dtype)
         self.x_host = torch.zeros(batch, in_channels, height, width, dtype=dtype).pin_memory()
@@ -119,7 +127,8 @@ class InferenceEngine:
 
     @torch.no_grad()
     def run(self, x_host: torch.Tensor) -> torch.Tensor:
-        """host (pinned or pageable) batch in -> host result out; H2D + forward + D2H on one stream."""
+        """host (pinned or pageable) batch in -> host result out; H2D + forward + D2H on one stream.
+        Returns the engine's reused pinned output buffer: the next run() overwrites it (clone() to keep a result)."""
         with torch.cuda.stream(self.stream):
             self.x_dev.copy_(x_host, non_blocking=True)
             if self.graph is not None:

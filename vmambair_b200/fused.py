@@ -21,12 +21,54 @@ from . import ops
 _DTYPES = (torch.float32, torch.bfloat16, torch.float16)
 
 
+_warned = set()
+
+
+def unsupported_reason(block, x: torch.Tensor):
+    """None when the fused kernels cover this call, else the first kernel limit it violates.  Mirrors the checks of the
+    launchers: LayerNorm / gate prologues keep the whole K resident (csrc/pixlin.cu pixlin_launch: K <= 384), the depthwise
+    conv indexes (batch, channel) planes on gridDim.y (csrc/api.cu vmb_dwconv3x3: batch * channels <= 65535), the channel
+    branch holds its (dc, C) problem in one CTA's shared memory (csrc/oss_ops.cu channel_launch), dstate <= 16."""
+    if not (x.is_cuda and x.dim() == 4):
+        return "not a CUDA (B,C,H,W) tensor"
+    if x.dtype not in _DTYPES:
+        return f"dtype {x.dtype}"
+    a = block.attn
+    if a.d_state > 16 or a.dc_state > 16:
+        return f"d_state {a.d_state} / dc_state {a.dc_state} > 16"
+    B, C = x.shape[0], x.shape[1]
+    h2 = block.ffn.project_in.weight.shape[0]
+    if C > 384:
+        return f"C = {C} > 384 (LayerNorm / gate prologue keeps K resident)"
+    if B * max(C, h2 // 2) > 65535 or B > 65535:
+        return f"batch * channels = {B * max(C, h2 // 2)} > 65535 (depthwise-conv grid)"
+    RN = a.dtc_rank + 2 * a.dc_state
+    dc = a.dc_inner
+    smem = 4 * (dc * C + 2 * RN * (C | 1) + 4 * dc * C + C + 64 + 2 * RN * dc + 2 * dc * a.dtc_rank + 5 * dc + 1)
+    if smem > 227 * 1024:
+        return f"channel branch needs {smem} B of shared memory"
+    return None
+
+
 def available(block, x: torch.Tensor) -> bool:
-    return x.is_cuda and x.dtype in _DTYPES and x.dim() == 4 and block.attn.d_state <= 16 and block.attn.dc_state <= 16
+    why = unsupported_reason(block, x)
+    if why is not None and x.is_cuda:
+        key = (why, tuple(x.shape[1:]))
+        if key not in _warned:  # once per (reason, shape): the composed torch + scan-operator path takes over, loudly
+            _warned.add(key)
+            import warnings
+            warnings.warn(f"vmambair_b200: fused OSS block not available ({why}); using the composed path for x{tuple(x.shape)}")
+    return why is None
 
 
 def _f32(t):
-    return None if t is None else t.detach().float().contiguous()
+    """fp32 kernel parameter; prefers the un-rounded fp32 master kept by engine.cast_for_inference"""
+    if t is None:
+        return None
+    m = getattr(t, "_vmb_master", None)
+    if m is not None and m.shape == t.shape and m.device == t.device:
+        return m.contiguous()
+    return t.detach().float().contiguous()
 
 
 def _prepare(block, dtype, device):

@@ -243,7 +243,8 @@ def selective_scan_fwd_grouped(us, deltas, Bs, Cs, revs, A, D, delta_bias, delta
         us[0].stride(0), us[0].stride(1), deltas[0].stride(0), deltas[0].stride(1), out.stride(0), out.stride(2),
         Bs[0].stride(0), Bs[0].stride(1), Cs[0].stride(0), Cs[0].stride(1), int(bool(delta_softplus)), _DT[us[0].dtype])
     es = us[0].element_size()
-    nbytes = es * b * L * (G * R + G * R + G * R + 2 * G * N)  # every operand / result once
+    n_u = len({t.data_ptr() for t in us})  # forward and reversed directions share one source tensor: counted once
+    nbytes = es * b * L * (n_u * R + G * R + G * R + 2 * G * N) + 4 * (G * R * N + 2 * G * R)  # every unique operand / result once
     _run("vmb_selective_scan_fwd_grouped", a, us[0], "scan_fwd", nbytes)
     return out
 
