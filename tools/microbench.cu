@@ -12,15 +12,17 @@ constexpr int ITERS = 2048;
 
 __device__ __forceinline__ float ex2f(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-enum { T_FFMA, T_FFMA2, T_FMUL2B, T_MUFU, T_MIX_SCAN, T_SHFL, T_LDS128, T_MIX_POLY, T_FADD2, T_IMAD, T_LOP, T_MIX2, T_COUNT };
+enum { T_FFMA, T_FFMA2, T_FMUL2B, T_MUFU, T_MIX_SCAN, T_SHFL, T_LDS128, T_MIX_POLY, T_FADD2, T_IMAD, T_LOP, T_MIX2, T_FMUL2S, T_FFMA2S, T_LDS_RB2, T_LDS_RB4, T_PASS1, T_COUNT };
 const char* kNames[] = {"ffma (3 regs)", "ffma2", "fmul2 (pair x pair)", "mufu.ex2", "mix: 2 mufu + 3 ffma2", "shfl.up", "lds.128 broadcast",
-                        "mix: 2 mufu + 7 ffma2", "fadd2", "imad", "lop3", "mix: 2 mufu + 3 ffma2 + 2 ffma + 1 lds128"};
-const int kInstrPerIter[] = {16, 16, 16, 16, 5 * 4, 16, 16, 9 * 4, 16, 16, 16, 8 * 4};
+                        "mix: 2 mufu + 7 ffma2", "fadd2", "imad", "lop3", "mix: 2 mufu + 3 ffma2 + 2 ffma + 1 lds128",
+                        "fmul2 (pair x broadcast scalar)", "ffma2 (pair, bcast scalar, pair)", "lds.128 16 addr x2 lanes, 144 B stride",
+                        "lds.128 8 addr x4 lanes, 144 B stride", "pass1-like: fmul2s, 2 mufu, fmul2s, ffma2 (loop-varying)"};
+const int kInstrPerIter[] = {16, 16, 16, 16, 5 * 4, 16, 16, 9 * 4, 16, 16, 16, 8 * 4, 16, 16, 16, 16, 5 * 8};
 
 template <int TEST>
 __global__ void __launch_bounds__(1024) bench(float* out, long long* cyc, float seed) {
-    __shared__ float4 sm[64];
-    if (threadIdx.x < 64) sm[threadIdx.x] = make_float4(seed, seed * 0.5f, seed * 0.25f, 1.f);
+    __shared__ float4 sm[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm[i] = make_float4(seed, seed * 0.5f, seed * 0.25f, 1.f);
     __syncthreads();
     float2 a[8], b[8];
 #pragma unroll
@@ -104,6 +106,33 @@ __global__ void __launch_bounds__(1024) bench(float* out, long long* cyc, float 
                 const float4 q = sm[(it + i) & 63];
                 a[i & 7].x += q.x;  // keep the load live (1 FADD per LDS; FADD rate >> LDS rate)
             }
+        } else if (TEST == T_FMUL2S) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = __fmul2_rn(a[i], make_float2(b[i].x, b[i].x));
+        } else if (TEST == T_FFMA2S) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = __ffma2_rn(a[i], make_float2(b[i].x, b[i].x), c);
+        } else if (TEST == T_LDS_RB2 || TEST == T_LDS_RB4) {
+            const int grp = (threadIdx.x & 31) / (TEST == T_LDS_RB2 ? 2 : 4);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float4 q = sm[grp * 9 + ((it + i) & 7)];
+                a[i & 7].x += q.x;
+            }
+        } else if (TEST == T_PASS1) {  // pass-1 shape with loop-varying dt (c.x changes every iteration): nothing hoistable
+            c.x += 1e-6f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float dti = c.x + b[i].y;
+                float2 e = __fmul2_rn(b[i], make_float2(dti, dti));
+                float2 aa = make_float2(ex2f(e.x), ex2f(e.y));
+                float2 bb = __fmul2_rn(b[(i + 1) & 7], make_float2(c.x, c.x));
+                a[0] = __ffma2_rn(aa, a[0], bb);
+            }
         } else if (TEST == T_IMAD) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) ia = ia * ib + i;
@@ -159,6 +188,11 @@ int main() {
     sweep<T_MIX2>(out, cyc, sms);
     sweep<T_SHFL>(out, cyc, sms);
     sweep<T_LDS128>(out, cyc, sms);
+    sweep<T_FMUL2S>(out, cyc, sms);
+    sweep<T_FFMA2S>(out, cyc, sms);
+    sweep<T_LDS_RB2>(out, cyc, sms);
+    sweep<T_LDS_RB4>(out, cyc, sms);
+    sweep<T_PASS1>(out, cyc, sms);
     sweep<T_IMAD>(out, cyc, sms);
     sweep<T_LOP>(out, cyc, sms);
     return 0;

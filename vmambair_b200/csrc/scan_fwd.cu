@@ -387,6 +387,10 @@ static int launch_t(const ScanFwdParams& p, cudaStream_t stream) {
 
 int scan_fwd_launch(const ScanFwdParams& p, int dtype, cudaStream_t stream) {
     VMB_CHECK((long)p.batch * p.dim < (1L << 31), "selective_scan_fwd: batch*dim too large");
+    {  // fast path: TMA-staged kernel (scan_fwd_tma.cu); this file keeps the generic shapes (unaligned rows, dstate > 16, short L)
+        int rb, ss;
+        if (scan_fwd_tma_pick(p, rb, ss)) return scan_fwd_tma_launch(p, dtype, rb, ss, stream);
+    }
     if (p.ndesc) {
         VMB_CHECK(p.vec_ok && p.npad == 16, "grouped scan: needs 16 B-aligned rows (L %% 8 == 0) and dstate <= 16");
         VMB_CHECK(p.ckpt == nullptr, "grouped scan: inference only (no checkpoints)");
