@@ -4,9 +4,11 @@ sources under /root/reference by oracle/build_ref.py) on identical inputs.
 
 Tolerances
   * fp32 whole-network vs oracle/oss_ref.net_forward: rtol 1e-3 / atol 1e-4 (the module bar of the block goldens);
-  * bf16 whole-network (bf16 weights + activations, fp32 scan state) vs the fp32 oracle: max |err| <= 0.1 and
-    mean |err| <= 0.01 on outputs in [0, 1] + O(1) residual -- bf16 has 8 significant bits (2^-8 = 3.9e-3 per
-    rounding), the network is 27 blocks deep;
+  * bf16 whole-network (bf16 weights + activations, fp32 scan state) vs the fp32 oracle: the yardstick is the oracle itself
+    evaluated with bf16 STORAGE (oss_ref.STORE_DTYPE: every tensor the pipeline keeps between kernels rounded to bf16, fp32
+    arithmetic) -- on the random-init 27-block bench net that emulation is already 0.028 mean / 0.18 max |err| off the fp32
+    oracle (outputs in [-0.5, 3]).  Bound: mean |err| <= 1.5 x and max |err| <= 3 x the emulation's, and absolutely
+    mean <= 0.05, max <= 0.5;
   * scan vs the reference CUDA kernel: the reference test's own tolerances (test_selective_scan.py:398-400, 490-502).
 """
 import importlib.util
@@ -34,10 +36,22 @@ def _oracle(net, x, kind):
         return oss_ref.net_forward(sd, x.float().cpu(), kind)
 
 
-def _bf16_bound(y, ref):
-    err = (y.float().cpu() - ref).abs()
+def _oracle_bf16_storage(net, x, kind):
+    """the fp32 oracle with bf16 storage emulation (see module docstring)"""
+    oss_ref.STORE_DTYPE = torch.bfloat16
+    try:
+        return _oracle(net, x, kind)
+    finally:
+        oss_ref.STORE_DTYPE = None
+
+
+def _bf16_bound(y, ref, emu):
     assert torch.isfinite(y).all()
-    assert err.max() <= 0.1 and err.mean() <= 0.01, (float(err.max()), float(err.mean()))
+    err = (y.float().cpu() - ref).abs()
+    e_emu = (emu - ref).abs()
+    msg = f"ours max {float(err.max()):.4f} mean {float(err.mean()):.5f}; bf16-storage oracle max {float(e_emu.max()):.4f} mean {float(e_emu.mean()):.5f}"
+    assert err.mean() <= 1.5 * e_emu.mean() + 1e-3 and err.max() <= 3.0 * e_emu.max() + 1e-2, msg
+    assert err.mean() <= 0.05 and err.max() <= 0.5, msg
 
 
 # ----------------------------------------------------------------------------- BASELINE configs[1]: the bench net
@@ -61,9 +75,10 @@ def test_bench_net_bf16_engine_vs_oracle():
     from vmambair_b200.engine import InferenceEngine
     net, x = _bench_net_and_input()
     ref = _oracle(net, x.to(torch.bfloat16), "sisr")  # same bf16-rounded input, fp32 arithmetic
+    emu = _oracle_bf16_storage(net, x.to(torch.bfloat16), "sisr")
     eng = InferenceEngine(net, 8, 64, 64, dtype=torch.bfloat16)
     y = eng.run(x.to(torch.bfloat16)).clone()
-    _bf16_bound(y, ref)
+    _bf16_bound(y, ref, emu)
 
 
 # ----------------------------------------------------------------------------- configs[3] / [4] geometry vs the oracle
@@ -83,8 +98,9 @@ def test_config45_geometry_vs_oracle(cls, kind, size, batch, dtype):
     else:
         from vmambair_b200.engine import InferenceEngine
         ref = _oracle(net, x.to(dtype), kind)
+        emu = _oracle_bf16_storage(net, x.to(dtype), kind)
         eng = InferenceEngine(net, batch, size, size, dtype=dtype, use_graph=False)
-        _bf16_bound(eng.run(x.to(dtype)).clone(), ref)
+        _bf16_bound(eng.run(x.to(dtype)).clone(), ref, emu)
 
 
 # ----------------------------------------------------------------------------- scan vs the reference CUDA kernel

@@ -76,7 +76,7 @@ __device__ __forceinline__ float2 log1p_series2(float2 e) {
 
 // MODE 0: plain operator   1: plain + checkpoints (training forward)   2: per-group sources, reversed walk (fused OSS block)
 template <typename in_t, int RB, int NW, int SS, int MODE>
-__global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 4)
+__global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 3)
     scan_fwd_tma_kernel(const ScanFwdParams p, const __grid_constant__ ScanTmaMaps maps) {
     pdl_trigger();
     pdl_wait();
@@ -232,28 +232,33 @@ __global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 4)
             sigma += dt[t] + dt[t + 1];
         }
 
-#pragma unroll 1
-        for (int np = sp * NPW; np < (sp + 1) * NPW; ++np) {
-            const int n0 = 2 * np;
-            const float2 A2 = *reinterpret_cast<const float2*>(&sA[r * 16 + n0]);
+        // ---- state-pair loop, software-pipelined: the MUFU-heavy pass 1 of pair np+1 (decay factors a = ex2(A dt), local end
+        // state) runs inside the same unrolled position loop as the FMA-heavy pass 2 of pair np (true states, y += C h); each a2[t]
+        // register is overwritten by the next pair's factor right after pass 2 consumed it, so no second array is live and
+        // every warp's instruction stream mixes XU, FMA and LDS work instead of alternating between MUFU-only and FMA-only phases.
+        float2 a2[T];
+        float2 hend = make_float2(0.f, 0.f), P2;
+        {
+            const int np = sp * NPW;
+            const float2 A2 = *reinterpret_cast<const float2*>(&sA[r * 16 + 2 * np]);
             const float4* __restrict__ bq = sB + np * SLOTS + sl * SEGQ;
-            const float4* __restrict__ cq = sC + np * SLOTS + sl * SEGQ;
-            // ---- pass 1: decay factors + local end state ----
-            float2 a2[T];
-            float2 hend = make_float2(0.f, 0.f);
 #pragma unroll
             for (int t = 0; t < T; t += 2) {
                 const float4 Bq = bq[t / 2];
-                float2 e0 = mul2(A2, make_float2(dt[t], dt[t]));
-                float2 e1 = mul2(A2, make_float2(dt[t + 1], dt[t + 1]));
+                const float2 e0 = mul2(A2, make_float2(dt[t], dt[t]));
+                const float2 e1 = mul2(A2, make_float2(dt[t + 1], dt[t + 1]));
                 a2[t] = make_float2(ex2(e0.x), ex2(e0.y));
                 a2[t + 1] = make_float2(ex2(e1.x), ex2(e1.y));
                 hend = fma2(a2[t], hend, mul2(make_float2(dtu[t], dtu[t]), make_float2(Bq.x, Bq.y)));
                 hend = fma2(a2[t + 1], hend, mul2(make_float2(dtu[t + 1], dtu[t + 1]), make_float2(Bq.z, Bq.w)));
             }
-            float2 P2 = mul2(A2, make_float2(sigma, sigma));
+            P2 = mul2(A2, make_float2(sigma, sigma));
             P2 = make_float2(ex2(P2.x), ex2(P2.y));
-            // ---- inclusive scan over the segments held by this warp ----
+        }
+#pragma unroll 1
+        for (int np = sp * NPW; np < (sp + 1) * NPW; ++np) {
+            const int n0 = 2 * np;
+            // ---- inclusive scan over the segments held by this warp (pair np) ----
 #pragma unroll
             for (int o = RB; o < 32; o <<= 1) {
                 const float2 Pp = shfl_up2(P2, o), Hp = shfl_up2(hend, o);
@@ -272,15 +277,44 @@ __global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 4)
             float2 h = fma2(Pe, st, He);
             __syncwarp();
             if (sl == SEGW - 1) *carry = fma2(P2, st, hend);
-            // ---- pass 2: true states, output contraction ----
+            const float4* __restrict__ bq = sB + np * SLOTS + sl * SEGQ;
+            const float4* __restrict__ cq = sC + np * SLOTS + sl * SEGQ;
+            if (np + 1 < (sp + 1) * NPW) {
+                // ---- pass 2 of pair np fused with pass 1 of pair np+1 ----
+                const float2 A2n = *reinterpret_cast<const float2*>(&sA[r * 16 + n0 + 2]);
+                const float4* __restrict__ bqn = bq + SLOTS;
+                float2 hn = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int t = 0; t < T; t += 2) {
-                const float4 Bq = bq[t / 2];
-                const float4 Cq = cq[t / 2];
-                h = fma2(a2[t], h, mul2(make_float2(dtu[t], dtu[t]), make_float2(Bq.x, Bq.y)));
-                y[t] = fmaf(h.y, Cq.y, fmaf(h.x, Cq.x, y[t]));
-                h = fma2(a2[t + 1], h, mul2(make_float2(dtu[t + 1], dtu[t + 1]), make_float2(Bq.z, Bq.w)));
-                y[t + 1] = fmaf(h.y, Cq.w, fmaf(h.x, Cq.z, y[t + 1]));
+                for (int t = 0; t < T; t += 2) {
+                    const float4 Bq = bq[t / 2];
+                    const float4 Cq = cq[t / 2];
+                    const float4 Bn = bqn[t / 2];
+                    const float2 du0 = make_float2(dtu[t], dtu[t]), du1 = make_float2(dtu[t + 1], dtu[t + 1]);
+                    h = fma2(a2[t], h, mul2(du0, make_float2(Bq.x, Bq.y)));
+                    y[t] = fmaf(h.y, Cq.y, fmaf(h.x, Cq.x, y[t]));
+                    const float2 e0 = mul2(A2n, make_float2(dt[t], dt[t]));
+                    a2[t] = make_float2(ex2(e0.x), ex2(e0.y));
+                    hn = fma2(a2[t], hn, mul2(du0, make_float2(Bn.x, Bn.y)));
+                    h = fma2(a2[t + 1], h, mul2(du1, make_float2(Bq.z, Bq.w)));
+                    y[t + 1] = fmaf(h.y, Cq.w, fmaf(h.x, Cq.z, y[t + 1]));
+                    const float2 e1 = mul2(A2n, make_float2(dt[t + 1], dt[t + 1]));
+                    a2[t + 1] = make_float2(ex2(e1.x), ex2(e1.y));
+                    hn = fma2(a2[t + 1], hn, mul2(du1, make_float2(Bn.z, Bn.w)));
+                }
+                hend = hn;
+                P2 = mul2(A2n, make_float2(sigma, sigma));
+                P2 = make_float2(ex2(P2.x), ex2(P2.y));
+            } else {
+                // ---- last pair of this warp: pass 2 only ----
+#pragma unroll
+                for (int t = 0; t < T; t += 2) {
+                    const float4 Bq = bq[t / 2];
+                    const float4 Cq = cq[t / 2];
+                    h = fma2(a2[t], h, mul2(make_float2(dtu[t], dtu[t]), make_float2(Bq.x, Bq.y)));
+                    y[t] = fmaf(h.y, Cq.y, fmaf(h.x, Cq.x, y[t]));
+                    h = fma2(a2[t + 1], h, mul2(make_float2(dtu[t + 1], dtu[t + 1]), make_float2(Bq.z, Bq.w)));
+                    y[t + 1] = fmaf(h.y, Cq.w, fmaf(h.x, Cq.z, y[t + 1]));
+                }
             }
             if (MODE == 1 && l0 < L && ((l0 + T) % kScanCkpt) == 0) {
                 float* ck = p.ckpt + (((int64_t)b * p.dim + d) * p.n_ckpt + ((l0 + T) / kScanCkpt - 1)) * N + n0;
@@ -383,12 +417,15 @@ static int launch_tma3(const ScanFwdParams& p, const ScanTmaMaps& maps, cudaStre
     return p.ckpt ? launch_tma4<in_t, RB, NW, SS, 1>(p, maps, stream) : launch_tma4<in_t, RB, NW, SS, 0>(p, maps, stream);
 }
 
+// 4-warp CTAs, three resident per SM: 384 CTAs at (8, 384, 4096) spread 2-3 per SM (8-warp CTAs: 192 on 148 SMs, 1-2 per SM)
+constexpr int kTmaWarps = 4;
+
 template <typename in_t, int RB>
 static int launch_tma2(const ScanFwdParams& p, const ScanTmaMaps& maps, int ss, cudaStream_t stream) {
     switch (ss) {
-        case 4: return launch_tma3<in_t, RB, 8, 4>(p, maps, stream);
-        case 2: return launch_tma3<in_t, RB, 8, 2>(p, maps, stream);
-        default: return launch_tma3<in_t, RB, 8, 1>(p, maps, stream);
+        case 4: return launch_tma3<in_t, RB, kTmaWarps, 4>(p, maps, stream);
+        case 2: return launch_tma3<in_t, RB, kTmaWarps, 2>(p, maps, stream);
+        default: return launch_tma3<in_t, RB, kTmaWarps, 1>(p, maps, stream);
     }
 }
 
@@ -422,13 +459,13 @@ bool scan_fwd_tma_pick(const ScanFwdParams& p, int& rb, int& ss) {
         const int x = atoi(v);
         if (x == 1 || x == 2 || x == 4) ss = x;
     }
-    while (rb > 2 && rpg % (rb * 8 / ss) != 0) rb >>= 1;
-    return rpg % (rb * 8 / ss) == 0;
+    while (rb > 2 && rpg % (rb * kTmaWarps / ss) != 0) rb >>= 1;
+    return rpg % (rb * kTmaWarps / ss) == 0;
 }
 
 int scan_fwd_tma_launch(const ScanFwdParams& p, int dtype, int rb, int ss, cudaStream_t stream) {
     ScanTmaMaps maps;
-    const uint32_t chunk = 32 / rb * T, rows = rb * 8 / ss;
+    const uint32_t chunk = 32 / rb * T, rows = rb * kTmaWarps / ss;
     const uint32_t box_io[4] = {chunk, rows, 1, 1}, box_bc[4] = {chunk, 16, 1, 1};
     if (p.ndesc) {
         for (int g = 0; g < p.ndesc; ++g) {
