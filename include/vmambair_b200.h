@@ -121,8 +121,9 @@ typedef struct {
 } vmb_pixlin_args;
 int vmb_pixlin(const vmb_pixlin_args* a, void* stream);
 
-/* depthwise 3x3 (pad 1) + bias, then mode 0: SiLU (SS2D_1.conv2d+act :490-491) or mode 1: gelu(conv[c]) *
- * conv[c+C_out] (FeedForward.dwconv + gate :215-216).  w: (channels, 9) fp32. */
+/* depthwise 3x3 (pad 1) + bias, then mode 0: SiLU (SS2D_1.conv2d+act :490-491), mode 1: gelu(conv[c]) *
+ * conv[c+C_out] (FeedForward.dwconv + gate :215-216), or mode 2: nothing (the transposed conv of the backward pass, called
+ * with the spatially flipped taps).  w: (channels, 9) fp32. */
 typedef struct {
     const void* x; const float* w; const float* bias; void* out;
     int batch, c_out, H, W, mode;
@@ -138,6 +139,7 @@ typedef struct {
     int batch, rows, H, W;
     int64_t src_bs, src_rs, out_bs;
     int dtype;
+    int64_t out_ks; /* element stride between the four directions of `out` (0: rows * H * W, dense) */
 } vmb_cross_scan_args;
 int vmb_cross_scan(const vmb_cross_scan_args* a, void* stream);
 
@@ -163,6 +165,8 @@ typedef struct {
     void* workspace;
     int in_place_order; /* 0: ys[k] in scan order (k=2,3 reversed); 1: ys[0],ys[2] in natural (H,W) pixel order and
                            ys[1],ys[3] in transposed (W,H) pixel order (outputs of vmb_selective_scan_fwd_grouped) */
+    int z_preact;       /* 0: z already holds SiLU(z) (inference: the in_conv epilogue applied it); 1: z is the pre-activation
+                           and SiLU is applied here (training: the backward needs the pre-activation) */
 } vmb_merge_args;
 int vmb_merge_norm_gate(const vmb_merge_args* a, void* stream);
 int64_t vmb_merge_workspace_bytes(int batch, int C, int H, int W);
@@ -178,6 +182,64 @@ typedef struct {
     int batch, C, dc, Rc, N;
 } vmb_channel_args;
 int vmb_channel_branch(const vmb_channel_args* a, void* stream);
+
+/* ---- training path: backward of the fused stages (autograd of the modules above) ----------------
+ * The 1x1-conv data gradients are vmb_pixlin with the transposed weight, the scan gradient is vmb_selective_scan_bwd,
+ * the direction gathers are vmb_cross_scan (pi_k^-1 = pi_k with H and W swapped).  Parameter gradients (dw, db, ...) are
+ * fp32 and ACCUMULATED into (the caller zero-fills), like the reference's autograd accumulates .grad. */
+
+/* y = LayerNorm_C(x) per pixel, materialised (the weight-gradient GEMMs of in_conv / project_in need it);
+ * mode 1: WithBias, 2: BiasFree (MambaSISR6_arch.py:166-195).  y and/or stats (B, L, 2) = (mean, rstd) may be NULL. */
+typedef struct {
+    const void* x; const float* w; const float* b; void* y; float* stats;
+    int batch, C, L, mode;
+    int64_t x_bs, x_cs, y_bs, y_cs;
+    int dtype;
+} vmb_ln_fwd_args;
+int vmb_layernorm_fwd(const vmb_ln_fwd_args* a, void* stream);
+
+/* dx = LayerNorm backward of g (gradient w.r.t. the LayerNorm output) [+ add]; dw += sum g*xhat, db += sum g (dw/db may be NULL).
+ * stats: fp32 scratch (B, L, 2), written. */
+typedef struct {
+    const void* x; const void* g; const void* add; const float* w; void* dx; float* dw; float* db; float* stats;
+    int batch, C, L, mode;
+    int64_t x_bs, x_cs, g_bs, g_cs, a_bs, a_cs, dx_bs, dx_cs;
+    int dtype;
+} vmb_ln_bwd_args;
+int vmb_layernorm_bwd(const vmb_ln_bwd_args* a, void* stream);
+
+/* backward of vmb_merge_norm_gate (z_preact = 1): merged / stats = the forward's workspace (fp32 merged scan output (B,C,L) and the
+ * per-pixel (sum, sum of squares) over C); dy2 (B,C,L) dense, dpooled (B,C) fp32 or NULL.
+ * -> dm (B,C,L) dense: gradient w.r.t. the merged scan output (gathered into the four scan orders by vmb_cross_scan),
+ *    dz: gradient w.r.t. the pre-activation z, dw/db += out_norm parameter gradients. */
+typedef struct {
+    const float* merged; const float* stats; const void* z; const void* dy2; const float* dpooled;
+    const float* w; const float* b; void* dm; void* dz; float* dw; float* db;
+    int batch, C, L;
+    int64_t z_bs, z_cs, dz_bs, dz_cs;
+    int dtype;
+} vmb_merge_bwd_args;
+int vmb_merge_norm_gate_bwd(const vmb_merge_bwd_args* a, void* stream);
+
+/* backward of vmb_dwconv3x3 up to the conv output: dv = gradient w.r.t. the conv result before the activation
+ * (mode 0: g * silu'(v); mode 1: dv[c] = g * v2 * gelu'(v1), dv[c+c_out] = g * gelu(v1)); the conv itself is recomputed from x.
+ * dw (channels, 9) / dbias (channels) fp32 accumulated when dw != NULL.  The input gradient is vmb_dwconv3x3(dv, flipped taps, mode 2). */
+typedef struct {
+    const void* x; const float* w; const float* bias; const void* g; void* dv; float* dw; float* dbias;
+    int batch, c_out, H, W, mode;
+    int64_t x_bs, x_cs, g_bs, g_cs, dv_bs, dv_cs;
+    int dtype;
+} vmb_dwconv_bwd_args;
+int vmb_dwconv3x3_bwd(const vmb_dwconv_bwd_args* a, void* stream);
+
+/* backward of the channel gate in front of out_conv (vmb_pixlin gate_mode 1: y*(1+c), 2: y+c): dyg, y2 (B,C,L) dense ->
+ * dy2 (B,C,L), dgate (B,C) fp32 (fully written). */
+typedef struct {
+    const void* dyg; const void* y2; const float* gate; void* dy2; float* dgate;
+    int batch, C, L, mode;
+    int dtype;
+} vmb_gate_bwd_args;
+int vmb_channel_gate_bwd(const vmb_gate_bwd_args* a, void* stream);
 
 #ifdef __cplusplus
 }

@@ -145,7 +145,7 @@ extern "C" int vmb_cross_scan(const vmb_cross_scan_args* a, void* stream) {
     VMB_CHECK(a && a->src[0] && a->src[1] && a->src[2] && a->src[3] && a->out, "cross_scan: null pointer");
     VMB_CHECK(dt_ok(a->dtype), "cross_scan: bad dtype");
     CrossScanParams p{{a->src[0], a->src[1], a->src[2], a->src[3]}, a->out, a->batch, a->rows, a->H, a->W, a->src_bs,
-                      a->src_rs, a->out_bs};
+                      a->src_rs, a->out_bs, a->out_ks > 0 ? a->out_ks : (int64_t)a->rows * a->H * a->W};
     return cross_scan_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
 }
 
@@ -157,7 +157,7 @@ extern "C" int vmb_merge_norm_gate(const vmb_merge_args* a, void* stream) {
     VMB_CHECK(a && a->ys && a->z && a->ln_w && a->ln_b && a->y2 && a->pooled, "merge: null pointer");
     VMB_CHECK(dt_ok(a->dtype), "merge: bad dtype");
     VMB_CHECK(a->batch > 0 && a->batch <= 65535, "merge: bad batch");
-    MergeParams p{a->ys, a->z, a->ln_w, a->ln_b, a->y2, a->pooled, a->batch, a->C, a->H, a->W, a->z_bs, a->z_cs, a->in_place_order, a->workspace};
+    MergeParams p{a->ys, a->z, a->ln_w, a->ln_b, a->y2, a->pooled, a->batch, a->C, a->H, a->W, a->z_bs, a->z_cs, a->in_place_order, a->workspace, a->z_preact};
     VMB_CHECK(a->workspace && aligned16(a->workspace), "merge: 16 B-aligned workspace of vmb_merge_workspace_bytes() required");
     return merge_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
 }

@@ -84,9 +84,9 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwParams p) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
         w0[i] = p.w[c * 9 + i];
-        w1[i] = p.mode ? p.w[(c + p.Cout) * 9 + i] : 0.f;
+        w1[i] = p.mode == 1 ? p.w[(c + p.Cout) * 9 + i] : 0.f;
     }
-    const float b0 = p.bias ? p.bias[c] : 0.f, b1 = (p.bias && p.mode) ? p.bias[c + p.Cout] : 0.f;
+    const float b0 = p.bias ? p.bias[c] : 0.f, b1 = (p.bias && p.mode == 1) ? p.bias[c + p.Cout] : 0.f;
     if (p.vec_ok) {
         constexpr int V = Vec<in_t>::N;
         for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 8; i < L; i += gridDim.x * blockDim.x * 8) {
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwParams p) {
             if (p.mode == 0) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) a0[j] = silu2(a0[j]);
-            } else {
+            } else if (p.mode == 1) {
                 dw_strip<in_t>(xb + (int64_t)(c + p.Cout) * p.x_cs, w1, h, w, p.H, p.W, b1, a1);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) a0[j] = gelu_exact(a0[j]) * a1[j];
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwParams p) {
         float v = dw_at<in_t>(xb + (int64_t)c * p.x_cs, w0, h, w, p.H, p.W) + b0;
         if (p.mode == 0) {
             v = silu2(v);
-        } else {
+        } else if (p.mode == 1) {
             const float g = dw_at<in_t>(xb + (int64_t)(c + p.Cout) * p.x_cs, w1, h, w, p.H, p.W) + b1;
             v = gelu_exact(v) * g;
         }
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_rows4_kernel(const DwParams p, 
         for (int o = 0; o < 4; ++o)
 #pragma unroll
             for (int i = 0; i < 8; ++i) a0[o][i] = silu2(a0[o][i]);
-    } else {
+    } else if (p.mode == 1) {
 #pragma unroll
         for (int o = 0; o < 4; ++o)
 #pragma unroll
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256) cross_scan_kernel(const CrossScanParams p
     }
     __syncthreads();
     in_t* __restrict__ o = reinterpret_cast<in_t*>(p.out) + (int64_t)b * p.out_bs;
-    const int64_t dir_stride = (int64_t)p.rows * L;
+    const int64_t dir_stride = p.out_ks;
     for (int j = ty; j < 32; j += 8) {
         // row-major orders: l = h*W + w (k=0) and its reversal (k=2); threads along w
         int h = h0 + j, w = w0 + tx;
@@ -485,7 +485,8 @@ __global__ void __launch_bounds__(256) norm_gate_pool_kernel(const MergeParams p
         const float nrm = (m[l] - mu) * rstd * lw + lb;
         // the reference rounds y1 to the activation dtype before the gate (.to(x.dtype), :434)
         const float n_r = to_f32<in_t>(from_f32<in_t>(nrm));
-        const in_t y = from_f32<in_t>(n_r * to_f32<in_t>(z[l]));
+        const float zv = to_f32<in_t>(z[l]);
+        const in_t y = from_f32<in_t>(n_r * (p.z_preact ? silu2(zv) : zv));
         o[l] = y;
         acc += to_f32<in_t>(y);
     }

@@ -21,7 +21,7 @@ struct DwParams {
 struct CrossScanParams {
     const void* src[4]; void* out;
     int B, rows, H, W;
-    int64_t src_bs, src_rs, out_bs;
+    int64_t src_bs, src_rs, out_bs, out_ks;
 };
 struct MergeParams {
     const void* ys; const void* z; const float* ln_w; const float* ln_b; void* y2; float* pooled;
@@ -29,6 +29,7 @@ struct MergeParams {
     int64_t z_bs, z_cs;
     int in_place_order;
     void* ws;  // fp32 scratch: B*C*L merged values + 2*B*L per-pixel statistics
+    int z_preact;
 };
 struct TransposeParams {
     const void* x; void* out;

@@ -145,7 +145,6 @@ __global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 3)
     const float bias = p.bias ? p.bias[d] : 0.f;
     __syncthreads();  // barrier initialised before anyone polls it
     uint32_t phase = 0;
-
     for (int c0 = 0; c0 < L; c0 += CHUNK) {
         const int l0 = c0 + sl * T;
         const int valid = min(max(L - l0, 0), T);
@@ -447,8 +446,10 @@ bool scan_fwd_tma_pick(const ScanFwdParams& p, int& rb, int& ss) {
     const int rpg = p.rows_per_group;
     const long rows = (long)p.batch * p.dim;
     const long want = 1184;  // >= 2 warps per scheduler on 148 SMs
-    rb = 8;
-    while (rb > 2 && rows / rb < want) rb >>= 1;
+    // measured (tools/scan_sweep.py, profiles/scan_sweep_r2.md): rb = 2 wins at every batch size -- with more rows per warp the
+    // B/C tile reads shrink but the warp count drops, and the MUFU + LDS + SHFL instructions of a warp all queue on one path
+    rb = 2;
+    (void)env_int;
     ss = 1;
     while (ss < 4 && rows / rb * ss < want) ss <<= 1;
     if (const char* v = getenv("VMB_SCAN_RB")) {
@@ -463,7 +464,21 @@ bool scan_fwd_tma_pick(const ScanFwdParams& p, int& rb, int& ss) {
     return rpg % (rb * kTmaWarps / ss) == 0;
 }
 
-int scan_fwd_tma_launch(const ScanFwdParams& p, int dtype, int rb, int ss, cudaStream_t stream) {
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+int scan_fwd_tma_launch(const ScanFwdParams& p_in, int dtype, int rb, int ss, cudaStream_t stream) {
+    ScanFwdParams p = p_in;
+    {
+        static const int sms = [] {
+            int dev = 0, n = 148;
+            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+            return n > 0 ? n : 148;
+        }();
+        p.num_sms = sms;
+    }
     ScanTmaMaps maps;
     const uint32_t chunk = 32 / rb * T, rows = rb * kTmaWarps / ss;
     const uint32_t box_io[4] = {chunk, rows, 1, 1}, box_bc[4] = {chunk, 16, 1, 1};

@@ -28,6 +28,7 @@ struct ScanFwdParams {
     bool vec_ok;
     int ndesc;              // 0: flat tensors (B0 operator); else = G <= 4 group descriptors (strides shared, per-group bases)
     ScanGroupDesc grp[4];
+    int num_sms;
 };
 
 struct ScanBwdParams {

@@ -1,0 +1,38 @@
+// Internal parameter blocks of the training-path (backward) kernels; see include/vmambair_b200.h for the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vmb {
+struct LnFwdParams {
+    const void* x; const float* w; const float* b; void* y; float* stats;
+    int B, C, L, mode;
+    int64_t x_bs, x_cs, y_bs, y_cs;
+};
+struct LnBwdParams {
+    const void* x; const void* g; const void* add; const float* w; void* dx; float* dw; float* db; float* stats;
+    int B, C, L, mode;
+    int64_t x_bs, x_cs, g_bs, g_cs, a_bs, a_cs, dx_bs, dx_cs;
+};
+struct MergeBwdParams {
+    const float* merged; const float* stats; const void* z; const void* dy2; const float* dpooled;
+    const float* w; const float* b; void* dm; void* dz; float* dw; float* db;
+    int B, C, L;
+    int64_t z_bs, z_cs, dz_bs, dz_cs;
+};
+struct DwBwdParams {
+    const void* x; const float* w; const float* bias; const void* g; void* dv; float* dwgt; float* dbias;
+    int B, Cout, H, W, mode;
+    int64_t x_bs, x_cs, g_bs, g_cs, dv_bs, dv_cs;
+};
+struct GateBwdParams {
+    const void* dyg; const void* y2; const float* gate; void* dy2; float* dgate;
+    int B, C, L, mode;
+};
+int ln_fwd_launch(const LnFwdParams& p, int dtype, cudaStream_t stream);
+int ln_bwd_launch(const LnBwdParams& p, int dtype, cudaStream_t stream);
+int merge_bwd_launch(const MergeBwdParams& p, int dtype, cudaStream_t stream);
+int dwconv_bwd_launch(const DwBwdParams& p, int dtype, cudaStream_t stream);
+int dwconv_wgrad_launch(const DwBwdParams& p, int dtype, cudaStream_t stream);
+int gate_bwd_launch(const GateBwdParams& p, int dtype, cudaStream_t stream);
+}  // namespace vmb
