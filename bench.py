@@ -177,8 +177,6 @@ def run_infer(args):
     rank, local, world = env_rank()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    if world > 1:
-        torch.distributed.init_process_group("nccl", device_id=dev)
     B = B_PER_GPU_INFER
     chains = int(os.environ.get("VMB_CHAINS", "1"))
     lowres = int(os.environ.get("VMB_LOWRES_CHAINS", "1"))
@@ -280,9 +278,21 @@ def run_infer(args):
                              "note": "the oracle itself evaluated with bf16 storage is 0.028 mean / 0.18 max off its fp32 result on this net (tests/test_bench_parity_gpu.py)"}
             if float(err.max()) > 0.5 or float(err.mean()) > 0.05:
                 raise SystemExit(f"bench.py: benchmarked output off the oracle: {out['parity']}")
-        print(json.dumps(out), flush=True)
-    if world > 1:
-        torch.distributed.destroy_process_group()
+    del eng, eager
+    torch.cuda.empty_cache()
+    return out
+
+
+def train_record(args):
+    """BASELINE configs[2] (the training step: the one path with a collective) as a sub-record of the default line, so the
+    driver's 1 -> 8 GPU sweep carries a training-scaling curve next to the collective-free inference one."""
+    from vmambair_b200.train_bench import run_train
+    a = argparse.Namespace(**vars(args))
+    a.steps, a.warmup = min(args.steps, 10), 3
+    t = run_train(a, build_net, ClockSampler, env_rank, dist_max, barrier, peaks, sample_clocks=False)
+    keep = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "config", "e2e", "gpu_launches",
+            "collective", "loss_last", "roofline")
+    return {k: t[k] for k in keep}
 
 
 def main():
@@ -296,15 +306,29 @@ def main():
                     help="inference net: light = class-default MambaSISR6 [6,2,2,1]+6 (BASELINE configs[1]); full = the YAML's "
                          "[15,1,1,1]+15 (SURVEY.md 8d asks for both)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step sub-record of the default run")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path); use --impl reference for the CPU oracle")
-    if args.workload == "train":
-        from vmambair_b200.train_bench import run_train
-        return run_train(args, build_net, ClockSampler, env_rank, dist_max, barrier, peaks)
-    return run_infer(args)
+    rank, local, world = env_rank()
+    if world > 1:
+        torch.cuda.set_device(local)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    try:
+        if args.workload == "train":
+            from vmambair_b200.train_bench import run_train
+            out = run_train(args, build_net, ClockSampler, env_rank, dist_max, barrier, peaks)
+        else:
+            out = run_infer(args)
+            if not args.no_train:
+                out["train"] = train_record(args)
+        if rank == 0:
+            print(json.dumps(out), flush=True)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -241,6 +241,22 @@ typedef struct {
 } vmb_gate_bwd_args;
 int vmb_channel_gate_bwd(const vmb_gate_bwd_args* a, void* stream);
 
+/* Fused Adam / AdamW step + gradient clipping + EMA over FLAT fp32 buffers of n elements (optimizer_g.step(), clip_grad_norm_,
+ * model_ema(): SRGAN/VmambaIR/models/MambaSISR_model.py:141-147, Deraining/basicsr/models/image_restoration_model.py:165-173,
+ * Deraining/basicsr/models/base_model.py:54-62).  grad is first multiplied by grad_scale (1/world after the all-reduce) and, when
+ * max_grad_norm > 0, by min(1, max_grad_norm / (||grad|| + 1e-6)).  state: 4 floats on the device, zero-initialised by the
+ * caller; state[0] is the step count, advanced by this call (so CUDA-graph replays keep the bias correction right).
+ * ema (NULL: none): ema = ema_decay * ema + (1 - ema_decay) * param.  zero_grad != 0 clears the gradient buffer. */
+typedef struct {
+    float* param; float* grad; float* exp_avg; float* exp_avg_sq; float* ema; float* state;
+    long n;
+    float lr, beta1, beta2, eps, weight_decay;
+    int decoupled_weight_decay;   /* 0: Adam (L2 added to the gradient), 1: AdamW */
+    float grad_scale, max_grad_norm, ema_decay;
+    int zero_grad;
+} vmb_adam_args;
+int vmb_fused_adam(const vmb_adam_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,90 @@
+"""GPU parity of the TRAINING path (vmambair_b200.fused_train: forward and backward of every fused stage on this library's
+kernels) against the reference-autograd goldens (tests/golden/block_*.npz: dx and every parameter gradient of the real
+reference MamberBlock) and against the composed torch path."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import vmambair_b200.archs as archs
+
+pytestmark = pytest.mark.gpu
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _load_block(golden_dir, tag, variant, dim):
+    z = np.load(os.path.join(golden_dir, f"block_{tag}.npz"))
+    blk = archs.MamberBlock(dim=dim, num_heads=1, ffn_expansion_factor=2.66, bias=False, LayerNorm_type="WithBias", variant=variant)
+    blk.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}, strict=True)
+    return blk.cuda(), z
+
+
+@pytest.mark.parametrize("tag,variant,dim", [("sisr_c48", "sisr", 48), ("realsr_c32", "realsr", 32)])
+def test_block_fused_training_path_matches_reference_autograd(golden_dir, tag, variant, dim):
+    """forward value, dx and all parameter gradients of the fused training path vs the goldens of the real reference block"""
+    archs.set_train_path("fused")
+    blk, z = _load_block(golden_dir, tag, variant, dim)
+    x = torch.from_numpy(z["x"]).cuda().requires_grad_()
+    y = blk(x)  # grad enabled -> fused_train
+    assert y.grad_fn is not None and "Tail" in type(y.grad_fn).__name__
+    torch.testing.assert_close(y.detach().cpu(), torch.from_numpy(z["y"]), rtol=1e-3, atol=1e-4)
+    y.backward(torch.from_numpy(z["dout"]).cuda())
+    ref = torch.from_numpy(z["dx"])
+    assert (x.grad.cpu() - ref).abs().max() <= 2e-3 * ref.abs().max() + 1e-5
+    for n, p in blk.named_parameters():
+        r = torch.from_numpy(z[f"grad/{n}"])
+        assert p.grad is not None, n
+        err = (p.grad.cpu() - r).abs().max()
+        if n.endswith("conv_cout.bias"):  # true gradient exactly 0 (constant added before channel_norm): both sides round-off
+            assert err < 2e-2, (n, float(err))
+            continue
+        assert err <= 3e-3 * r.abs().max().clamp_min(1e-6) + 1e-5, (n, float(err), float(r.abs().max()))
+
+
+@pytest.mark.parametrize("variant,dim", [("mamber32", 32), ("mamber33", 32)])
+def test_block_fused_training_path_matches_composed_autograd(variant, dim):
+    """additive channel gate (Mamber32) and dc_inner = 2 (Mamber33): fused training path vs torch autograd over the composed path"""
+    torch.manual_seed(3)
+    blk = archs.MamberBlock(dim=dim, num_heads=1, ffn_expansion_factor=2.66, bias=False, LayerNorm_type="WithBias", variant=variant).cuda()
+    x = torch.randn(2, dim, 16, 24, device="cuda")
+    dout = torch.randn(2, dim, 16, 24, device="cuda")
+    grads = {}
+    for path in ("fused", "compose"):
+        archs.set_train_path(path)
+        blk.zero_grad(set_to_none=True)
+        xx = x.clone().requires_grad_()
+        blk(xx).backward(dout)
+        grads[path] = [xx.grad.clone()] + [p.grad.clone() for p in blk.parameters()]
+    archs.set_train_path("fused")
+    names = ["x"] + [n for n, _ in blk.named_parameters()]
+    for n, a, b in zip(names, grads["fused"], grads["compose"]):
+        tol = 2e-2 if n.endswith("conv_cout.bias") else 3e-3 * float(b.abs().max().clamp_min(1e-6)) + 1e-5
+        assert float((a - b).abs().max()) <= tol, (n, float((a - b).abs().max()), float(b.abs().max()))
+
+
+def test_block_fused_training_bf16_close_to_fp32():
+    """bf16 activations / fp32 parameters (the autocast training configuration): gradients within bf16 noise of the fp32 run"""
+    torch.manual_seed(5)
+    archs.set_train_path("fused")
+    blk = archs.MamberBlock(dim=48, num_heads=1, ffn_expansion_factor=2.66, bias=False, LayerNorm_type="WithBias").cuda()
+    x = torch.randn(2, 48, 32, 32, device="cuda")
+    dout = torch.randn(2, 48, 32, 32, device="cuda")
+    res = {}
+    for dt in (torch.float32, torch.bfloat16):
+        blk.zero_grad(set_to_none=True)
+        xx = x.detach().to(dt).clone().requires_grad_()
+        y = blk(xx)
+        assert y.dtype == dt
+        y.backward(dout.to(dt))
+        res[dt] = (y.float(), xx.grad.float(), {n: p.grad.clone() for n, p in blk.named_parameters()})
+    y32, dx32, g32 = res[torch.float32]
+    y16, dx16, g16 = res[torch.bfloat16]
+    assert (y16 - y32).abs().max() < 0.1 and (dx16 - dx32).abs().max() <= 0.05 * dx32.abs().max() + 0.02
+    for n in g32:
+        if n.endswith("conv_cout.bias"):
+            continue
+        rel = float((g16[n] - g32[n]).norm() / g32[n].norm().clamp_min(1e-8))
+        assert rel < 0.08, (n, rel)

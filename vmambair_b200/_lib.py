@@ -63,7 +63,7 @@ class CrossScanArgs(C.Structure):
     _fields_ = [
         ("src", vp * 4), ("out", vp),
         ("batch", C.c_int), ("rows", C.c_int), ("H", C.c_int), ("W", C.c_int),
-        ("src_bs", i64), ("src_rs", i64), ("out_bs", i64), ("dtype", C.c_int),
+        ("src_bs", i64), ("src_rs", i64), ("out_bs", i64), ("dtype", C.c_int), ("out_ks", i64),
     ]
 
 
@@ -72,6 +72,7 @@ class MergeArgs(C.Structure):
         ("ys", vp), ("z", vp), ("ln_w", vp), ("ln_b", vp), ("y2", vp), ("pooled", vp),
         ("batch", C.c_int), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int),
         ("z_bs", i64), ("z_cs", i64), ("dtype", C.c_int), ("workspace", vp), ("in_place_order", C.c_int),
+        ("z_preact", C.c_int),
     ]
 
 
@@ -103,6 +104,44 @@ class ChannelArgs(C.Structure):
     ]
 
 
+class LnFwdArgs(C.Structure):
+    _fields_ = [("x", vp), ("w", vp), ("b", vp), ("y", vp), ("stats", vp),
+                ("batch", C.c_int), ("C", C.c_int), ("L", C.c_int), ("mode", C.c_int),
+                ("x_bs", i64), ("x_cs", i64), ("y_bs", i64), ("y_cs", i64), ("dtype", C.c_int)]
+
+
+class LnBwdArgs(C.Structure):
+    _fields_ = [("x", vp), ("g", vp), ("add", vp), ("w", vp), ("dx", vp), ("dw", vp), ("db", vp), ("stats", vp),
+                ("batch", C.c_int), ("C", C.c_int), ("L", C.c_int), ("mode", C.c_int),
+                ("x_bs", i64), ("x_cs", i64), ("g_bs", i64), ("g_cs", i64), ("a_bs", i64), ("a_cs", i64),
+                ("dx_bs", i64), ("dx_cs", i64), ("dtype", C.c_int)]
+
+
+class MergeBwdArgs(C.Structure):
+    _fields_ = [("merged", vp), ("stats", vp), ("z", vp), ("dy2", vp), ("dpooled", vp), ("w", vp), ("b", vp),
+                ("dm", vp), ("dz", vp), ("dw", vp), ("db", vp),
+                ("batch", C.c_int), ("C", C.c_int), ("L", C.c_int),
+                ("z_bs", i64), ("z_cs", i64), ("dz_bs", i64), ("dz_cs", i64), ("dtype", C.c_int)]
+
+
+class DwconvBwdArgs(C.Structure):
+    _fields_ = [("x", vp), ("w", vp), ("bias", vp), ("g", vp), ("dv", vp), ("dw", vp), ("dbias", vp),
+                ("batch", C.c_int), ("c_out", C.c_int), ("H", C.c_int), ("W", C.c_int), ("mode", C.c_int),
+                ("x_bs", i64), ("x_cs", i64), ("g_bs", i64), ("g_cs", i64), ("dv_bs", i64), ("dv_cs", i64), ("dtype", C.c_int)]
+
+
+class GateBwdArgs(C.Structure):
+    _fields_ = [("dyg", vp), ("y2", vp), ("gate", vp), ("dy2", vp), ("dgate", vp),
+                ("batch", C.c_int), ("C", C.c_int), ("L", C.c_int), ("mode", C.c_int), ("dtype", C.c_int)]
+
+
+class AdamArgs(C.Structure):
+    _fields_ = [("param", vp), ("grad", vp), ("exp_avg", vp), ("exp_avg_sq", vp), ("ema", vp), ("state", vp),
+                ("n", C.c_long), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float), ("decoupled_weight_decay", C.c_int),
+                ("grad_scale", C.c_float), ("max_grad_norm", C.c_float), ("ema_decay", C.c_float), ("zero_grad", C.c_int)]
+
+
 # every symbol include/vmambair_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "vmb_last_error": (C.c_char_p, []),
@@ -120,6 +159,12 @@ SYMBOLS = {
     "vmb_pixel_shuffle2_nhwc": (C.c_int, [C.POINTER(PixelShuffleArgs), vp]),
     "vmb_selective_scan_fwd_grouped": (C.c_int, [C.POINTER(ScanGroupedArgs), vp]),
     "vmb_channel_branch": (C.c_int, [C.POINTER(ChannelArgs), vp]),
+    "vmb_layernorm_fwd": (C.c_int, [C.POINTER(LnFwdArgs), vp]),
+    "vmb_layernorm_bwd": (C.c_int, [C.POINTER(LnBwdArgs), vp]),
+    "vmb_merge_norm_gate_bwd": (C.c_int, [C.POINTER(MergeBwdArgs), vp]),
+    "vmb_dwconv3x3_bwd": (C.c_int, [C.POINTER(DwconvBwdArgs), vp]),
+    "vmb_channel_gate_bwd": (C.c_int, [C.POINTER(GateBwdArgs), vp]),
+    "vmb_fused_adam": (C.c_int, [C.POINTER(AdamArgs), vp]),
 }
 
 

@@ -16,19 +16,32 @@ Reference classes mirrored (file:line in /root/reference):
 Two execution paths share the parameters:
   * `fused`  (CUDA, no-grad calls): the hand-written kernels (vmambair_b200.fused) -- if the CUDA library is missing a
     RuntimeError is raised; shapes outside the kernels' limits (fused.unsupported_reason) take `compose` with a warning;
+  * `fused_train` (CUDA, grad enabled; default): the fused stages with their hand-written backward kernels
+    (vmambair_b200.fused_train);
   * `compose`: the same math composed from torch ops + this repo's selective-scan operator with autograd
-    (used for training until every fused stage has its backward, and as the module-level cross-check).
+    (VMB_TRAIN_PATH=compose / set_train_path; the module-level cross-check and the fallback for unsupported shapes).
 """
 from __future__ import annotations
 
 import math
 import numbers
+import os
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from .selective_scan import selective_scan_fn
+
+# training path: "fused" = fused_train (native forward + backward kernels); "compose" = torch ops + the scan operator (round 1)
+_TRAIN_PATH = os.environ.get("VMB_TRAIN_PATH", "fused")
+
+
+def set_train_path(path: str) -> None:
+    global _TRAIN_PATH
+    assert path in ("fused", "compose")
+    _TRAIN_PATH = path
+
 
 VARIANTS = {
     # name: (dc_inner, channel rank ("dt_rank" -> same as dt_rank), has conv_cin/cout, gate)
@@ -212,9 +225,9 @@ class SS2D_1(nn.Module):
         y = out_y[:, 0].float() + inv_y[:, 0].float() + wh_y.float() + invwh_y.float()
         return self.out_norm(y.view(B, C, H, W)).to(x.dtype)
 
-    def cforward_core(self, xc):
-        b, d, h, w = xc.shape
-        pooled = xc.float().mean(dim=(2, 3)).to(xc.dtype)  # AdaptiveAvgPool2d(1) -> (b, d)
+    def cforward_pooled(self, pooled):
+        """channel-direction OSS on the pooled descriptor: pooled (b, d) channel means -> channel_norm output (b, d)
+        (reference cforward_corev1, MambaSISR6_arch.py:438-483, after its AdaptiveAvgPool2d)"""
         if hasattr(self, "conv_cin"):
             wci = self.conv_cin.weight.view(-1, 1)
             seq = pooled[:, None, :] * wci[None] + self.conv_cin.bias.view(1, -1, 1)  # (b, dc, L=d)
@@ -232,7 +245,12 @@ class SS2D_1(nn.Module):
         if hasattr(self, "conv_cout"):
             y = (y * self.conv_cout.weight.view(1, -1, 1).float()).sum(1, keepdim=True) + self.conv_cout.bias.float().view(1, 1, 1)
         y = y.transpose(1, 2).unsqueeze(-1)  # (b, L=d, 1, 1)
-        return self.channel_norm(y).to(xc.dtype)
+        return self.channel_norm(y).view(Bn, L)
+
+    def cforward_core(self, xc):
+        b, d, h, w = xc.shape
+        pooled = xc.float().mean(dim=(2, 3)).to(xc.dtype)  # AdaptiveAvgPool2d(1) -> (b, d)
+        return self.cforward_pooled(pooled).view(b, d, 1, 1).to(xc.dtype)
 
     def forward_compose(self, x):
         xz = self.in_conv(x)
@@ -262,10 +280,14 @@ class MamberBlock(nn.Module):
         return x + self.ffn(self.norm2(x))
 
     def forward(self, x):
-        if x.is_cuda and not torch.is_grad_enabled():
+        if x.is_cuda:
             from . import fused
-            if fused.available(self, x):
-                return fused.block_forward(self, x)
+            if not torch.is_grad_enabled():
+                if fused.available(self, x):
+                    return fused.block_forward(self, x)
+            elif _TRAIN_PATH == "fused" and fused.available(self, x):
+                from . import fused_train
+                return fused_train.block_forward(self, x)  # forward + backward of every stage on this library's kernels
         return self.forward_compose(x)
 
 

@@ -449,7 +449,6 @@ bool scan_fwd_tma_pick(const ScanFwdParams& p, int& rb, int& ss) {
     // measured (tools/scan_sweep.py, profiles/scan_sweep_r2.md): rb = 2 wins at every batch size -- with more rows per warp the
     // B/C tile reads shrink but the warp count drops, and the MUFU + LDS + SHFL instructions of a warp all queue on one path
     rb = 2;
-    (void)env_int;
     ss = 1;
     while (ss < 4 && rows / rb * ss < want) ss <<= 1;
     if (const char* v = getenv("VMB_SCAN_RB")) {
@@ -462,11 +461,6 @@ bool scan_fwd_tma_pick(const ScanFwdParams& p, int& rb, int& ss) {
     }
     while (rb > 2 && rpg % (rb * kTmaWarps / ss) != 0) rb >>= 1;
     return rpg % (rb * kTmaWarps / ss) == 0;
-}
-
-static int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
 }
 
 int scan_fwd_tma_launch(const ScanFwdParams& p_in, int dtype, int rb, int ss, cudaStream_t stream) {

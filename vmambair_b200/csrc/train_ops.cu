@@ -328,6 +328,60 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const GateBwdParams p) {
     if (threadIdx.x == 0) p.dgate[(int64_t)b * p.C + c] = t;
 }
 
+// ------------------------------------------------------------------------------------------ fused Adam(W) + clip + EMA
+// One pass over the flat fp32 parameter / gradient / moment buffers (reference: optimizer_g.step() + model_ema() +
+// clip_grad_norm_, SRGAN/VmambaIR/models/MambaSISR_model.py:141-147, Deraining/basicsr/models/image_restoration_model.py:165-173,
+// Deraining/basicsr/models/base_model.py:54-62) instead of ~1 500 per-tensor launches.  `state` (device, 4 floats):
+// [0] step count (incremented by the trailing 1-thread kernel: graph replays advance it), [1] sum of squared gradients.
+__global__ void __launch_bounds__(256) sqsum_kernel(const float* __restrict__ g, long n, float* __restrict__ state) {
+    __shared__ float sred[8];
+    float acc = 0.f;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) acc = fmaf(g[i], g[i], acc);
+    const float t = block_sum_256(acc, sred);
+    if (threadIdx.x == 0) atomicAdd(state + 1, t);
+}
+
+__global__ void __launch_bounds__(256) fused_adam_kernel(const AdamParams p) {
+    const float step = p.state[0] + 1.f;
+    const float bc1 = 1.f - powf(p.beta1, step), bc2 = 1.f - powf(p.beta2, step);
+    float gs = p.grad_scale;
+    if (p.max_norm > 0.f) {  // clip_grad_norm_: scale by max_norm / (total_norm + 1e-6), clamped to 1
+        const float total = sqrtf(p.state[1]) * p.grad_scale;
+        gs *= fminf(p.max_norm / (total + 1e-6f), 1.f);
+    }
+    const float step_size = p.lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < p.n; i += (long)gridDim.x * 256) {
+        float w = p.param[i];
+        float g = p.grad[i] * gs;
+        if (p.weight_decay != 0.f) {
+            if (p.decoupled) w -= p.lr * p.weight_decay * w;  // AdamW
+            else g = fmaf(p.weight_decay, w, g);                // Adam (L2)
+        }
+        const float m = fmaf(p.beta1, p.m[i], (1.f - p.beta1) * g);
+        const float v = fmaf(p.beta2, p.v[i], (1.f - p.beta2) * g * g);
+        p.m[i] = m;
+        p.v[i] = v;
+        w -= step_size * m / (sqrtf(v) * inv_sqrt_bc2 + p.eps);
+        p.param[i] = w;
+        if (p.ema) p.ema[i] = fmaf(p.ema_decay, p.ema[i], (1.f - p.ema_decay) * w);
+        if (p.zero_grad) p.grad[i] = 0.f;
+    }
+}
+
+__global__ void adam_step_inc_kernel(float* state) {
+    state[0] += 1.f;
+    state[1] = 0.f;
+}
+
+int fused_adam_launch(const AdamParams& p, cudaStream_t stream) {
+    const int blocks = (int)((p.n + 255) / 256 < 148 * 8 ? (p.n + 255) / 256 : 148 * 8);
+    if (p.max_norm > 0.f) sqsum_kernel<<<blocks, 256, 0, stream>>>(p.grad, p.n, p.state);
+    fused_adam_kernel<<<blocks, 256, 0, stream>>>(p);
+    adam_step_inc_kernel<<<1, 1, 0, stream>>>(p.state);
+    VMB_CUDA(cudaGetLastError());
+    return VMB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------- launchers
 #define VMB_DISPATCH(dtype, KERN, grid, block, ...)                                                    \
     switch (dtype) {                                                                                   \
@@ -423,6 +477,15 @@ extern "C" int vmb_dwconv3x3_bwd(const vmb_dwconv_bwd_args* a, void* stream) {
     int rc = dwconv_bwd_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
     if (rc != VMB_OK || !a->dw) return rc;
     return dwconv_wgrad_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vmb_fused_adam(const vmb_adam_args* a, void* stream) {
+    VMB_CHECK(a && a->param && a->grad && a->exp_avg && a->exp_avg_sq && a->state, "fused_adam: null pointer");
+    VMB_CHECK(a->n > 0 && a->lr >= 0.f && a->beta1 >= 0.f && a->beta1 < 1.f && a->beta2 >= 0.f && a->beta2 < 1.f && a->eps > 0.f,
+              "fused_adam: bad hyper-parameters");
+    AdamParams p{a->param, a->grad, a->exp_avg, a->exp_avg_sq, a->ema, a->state, a->n, a->lr, a->beta1, a->beta2, a->eps,
+                 a->weight_decay, a->decoupled_weight_decay, a->grad_scale, a->max_grad_norm, a->ema_decay, a->zero_grad};
+    return fused_adam_launch(p, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vmb_channel_gate_bwd(const vmb_gate_bwd_args* a, void* stream) {

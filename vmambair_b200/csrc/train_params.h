@@ -29,6 +29,15 @@ struct GateBwdParams {
     const void* dyg; const void* y2; const float* gate; void* dy2; float* dgate;
     int B, C, L, mode;
 };
+struct AdamParams {
+    float* param; float* grad; float* m; float* v; float* ema; float* state;
+    long n;
+    float lr, beta1, beta2, eps, weight_decay;
+    int decoupled;
+    float grad_scale, max_norm, ema_decay;
+    int zero_grad;
+};
+int fused_adam_launch(const AdamParams& p, cudaStream_t stream);
 int ln_fwd_launch(const LnFwdParams& p, int dtype, cudaStream_t stream);
 int ln_bwd_launch(const LnBwdParams& p, int dtype, cudaStream_t stream);
 int merge_bwd_launch(const MergeBwdParams& p, int dtype, cudaStream_t stream);

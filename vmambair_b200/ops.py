@@ -182,25 +182,30 @@ def pad_weight(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def dwconv3x3(x, w9, bias, c_out, H, W, mode):
-    """x: (B, Cin, H*W) view; mode 0: SiLU(dw(x[:c_out])); mode 1: gelu(dw(x[:c_out])) * dw(x[c_out:2c_out])."""
+def dwconv3x3(x, w9, bias, c_out, H, W, mode, out=None):
+    """x: (B, Cin, H*W) view; mode 0: SiLU(dw(x[:c_out])); mode 1: gelu(dw(x[:c_out])) * dw(x[c_out:2c_out]);
+    mode 2: dw(x[:c_out]) (no activation: the transposed conv of the backward pass, called with flipped taps)."""
     B = x.shape[0]
-    out = torch.empty((B, c_out, H * W), dtype=x.dtype, device=x.device)
+    if out is None:
+        out = torch.empty((B, c_out, H * W), dtype=x.dtype, device=x.device)
     a = _lib.DwconvArgs(_ptr(x), _ptr(w9), _ptr(bias), _ptr(out), B, c_out, H, W, mode,
                         x.stride(0), x.stride(1), out.stride(0), out.stride(1), _DT[x.dtype])
     _run("vmb_dwconv3x3", a, x, "dwconv")
     return out
 
 
-def cross_scan(srcs, rows, H, W):
-    """srcs: 4 views (B, rows, L) sharing strides -> (B, 4, rows, L) in scan order."""
+def cross_scan(srcs, rows, H, W, out=None):
+    """srcs: 4 views (B, rows, L) sharing strides -> (B, 4, rows, L) in scan order.  `out`: optional (B, 4, rows, L) view
+    (e.g. a channel slice of a wider tensor) with contiguous rows.  The inverse orders are the same call with H and W swapped."""
     s0 = srcs[0]
     B = s0.shape[0]
-    out = torch.empty((B, 4, rows, H * W), dtype=s0.dtype, device=s0.device)
+    if out is None:
+        out = torch.empty((B, 4, rows, H * W), dtype=s0.dtype, device=s0.device)
+    assert out.shape == (B, 4, rows, H * W) and out.stride(3) == 1 and out.stride(2) == H * W and out.dtype == s0.dtype
     arr = (C.c_void_p * 4)(*[t.data_ptr() for t in srcs])
     for t in srcs:
         assert t.stride() == s0.stride() and t.stride(2) == 1
-    a = _lib.CrossScanArgs(arr, _ptr(out), B, rows, H, W, s0.stride(0), s0.stride(1), out.stride(0), _DT[s0.dtype])
+    a = _lib.CrossScanArgs(arr, _ptr(out), B, rows, H, W, s0.stride(0), s0.stride(1), out.stride(0), _DT[s0.dtype], out.stride(1))
     _run("vmb_cross_scan", a, s0, "cross_scan")
     return out
 
@@ -249,17 +254,19 @@ def selective_scan_fwd_grouped(us, deltas, Bs, Cs, revs, A, D, delta_bias, delta
     return out
 
 
-def merge_norm_gate(ys, z, ln_w, ln_b, C_, H, W, in_place_order=False):
-    """ys: (B,4,C,L) contiguous; z: (B,C,L) view -> (y2 (B,C,L), pooled sums (B,C) fp32)."""
+def merge_norm_gate(ys, z, ln_w, ln_b, C_, H, W, in_place_order=False, z_preact=False, return_ws=False):
+    """ys: (B,4,C,L) contiguous; z: (B,C,L) view -> (y2 (B,C,L), pooled sums (B,C) fp32 [, workspace]).
+    z_preact: z holds the pre-activation (SiLU applied here); return_ws: also return the fp32 workspace (merged scan output
+    (B,C,L) followed by the per-pixel (sum, sum of squares)) that vmb_merge_norm_gate_bwd consumes."""
     B = ys.shape[0]
     assert ys.is_contiguous() and z.stride(2) == 1
     y2 = torch.empty((B, C_, H * W), dtype=ys.dtype, device=ys.device)
     pooled = torch.empty((B, C_), dtype=torch.float32, device=ys.device)
     ws = torch.empty(_lib.lib().vmb_merge_workspace_bytes(B, C_, H, W), dtype=torch.uint8, device=ys.device)
     a = _lib.MergeArgs(_ptr(ys), _ptr(z), _ptr(ln_w), _ptr(ln_b), _ptr(y2), _ptr(pooled), B, C_, H, W,
-                       z.stride(0), z.stride(1), _DT[ys.dtype], _ptr(ws), int(in_place_order))
+                       z.stride(0), z.stride(1), _DT[ys.dtype], _ptr(ws), int(in_place_order), int(z_preact))
     _run("vmb_merge_norm_gate", a, ys, "merge", 0, 2)
-    return y2, pooled
+    return (y2, pooled, ws) if return_ws else (y2, pooled)
 
 
 def channel_branch(pooled, inv_count, prm, C_):
@@ -270,3 +277,72 @@ def channel_branch(pooled, inv_count, prm, C_):
                          _ptr(prm["cout_b"]), _ptr(prm["cn_w"]), _ptr(prm["cn_b"]), _ptr(c), B, C_, prm["dc"], prm["Rc"], prm["N"])
     _run("vmb_channel_branch", a, pooled, "channel")
     return c
+
+
+# ----------------------------------------------------------------------------- training path: backward stages
+def layernorm_fwd(x, mode, w, b):
+    """x: (B,C,L) view -> LayerNorm over C per pixel, materialised (B,C,L) contiguous (mode 1 WithBias / 2 BiasFree)."""
+    B, C_, L = x.shape
+    assert x.stride(2) == 1
+    y = torch.empty((B, C_, L), dtype=x.dtype, device=x.device)
+    a = _lib.LnFwdArgs(_ptr(x), _ptr(w), _ptr(b), _ptr(y), None, B, C_, L, mode, x.stride(0), x.stride(1), y.stride(0), y.stride(1),
+                       _DT[x.dtype])
+    _run("vmb_layernorm_fwd", a, x, "ln_fwd")
+    return y
+
+
+def layernorm_bwd(x, g, mode, w, add=None, need_param_grads=True):
+    """-> (dx (B,C,L), dw (C) fp32, db (C) fp32 | None): LayerNorm backward of g [+ add] (the residual branch's gradient)."""
+    B, C_, L = x.shape
+    assert x.stride(2) == 1 and g.stride(2) == 1 and g.dtype == x.dtype and (add is None or (add.stride(2) == 1 and add.dtype == x.dtype))
+    dx = torch.empty((B, C_, L), dtype=x.dtype, device=x.device)
+    stats = torch.empty((B, L, 2), dtype=torch.float32, device=x.device)
+    dw = torch.zeros(C_, dtype=torch.float32, device=x.device) if need_param_grads else None
+    db = torch.zeros(C_, dtype=torch.float32, device=x.device) if (need_param_grads and mode == 1) else None
+    a = _lib.LnBwdArgs(_ptr(x), _ptr(g), _ptr(add), _ptr(w), _ptr(dx), _ptr(dw), _ptr(db), _ptr(stats), B, C_, L, mode,
+                       x.stride(0), x.stride(1), g.stride(0), g.stride(1), add.stride(0) if add is not None else 0,
+                       add.stride(1) if add is not None else 0, dx.stride(0), dx.stride(1), _DT[x.dtype])
+    _run("vmb_layernorm_bwd", a, x, "ln_bwd", 0, 2 if need_param_grads else 1)
+    return dx, dw, db
+
+
+def merge_norm_gate_bwd(ws, z, dy2, dpooled, ln_w, ln_b, C_, L, dz_out):
+    """backward of merge_norm_gate(z_preact=True).  ws: the forward's workspace; dy2 (B,C,L) contiguous; dpooled (B,C) fp32|None;
+    dz_out: (B,C,L) view receiving the gradient w.r.t. the pre-activation z.  -> (dm (B,C,L), d ln_w, d ln_b)."""
+    B = dy2.shape[0]
+    assert dy2.is_contiguous() and z.stride(2) == 1 and dz_out.stride(2) == 1
+    merged = ws.view(torch.float32)
+    stats = merged[B * C_ * L:]
+    dm = torch.empty((B, C_, L), dtype=dy2.dtype, device=dy2.device)
+    dw = torch.zeros(C_, dtype=torch.float32, device=dy2.device)
+    db = torch.zeros(C_, dtype=torch.float32, device=dy2.device)
+    a = _lib.MergeBwdArgs(_ptr(merged), _ptr(stats), _ptr(z), _ptr(dy2), _ptr(dpooled), _ptr(ln_w), _ptr(ln_b), _ptr(dm), _ptr(dz_out),
+                          _ptr(dw), _ptr(db), B, C_, L, z.stride(0), z.stride(1), dz_out.stride(0), dz_out.stride(1), _DT[dy2.dtype])
+    _run("vmb_merge_norm_gate_bwd", a, dy2, "merge_bwd", 0, 2)
+    return dm, dw, db
+
+
+def dwconv3x3_bwd(x, w9, bias, g, c_out, H, W, mode):
+    """backward of dwconv3x3 (mode 0 / 1) up to the conv output: -> (dv (B, channels, L), dw9 (channels, 9) fp32, dbias (channels) fp32|None);
+    the input gradient is dwconv3x3(dv, w9.flip(-1), None, channels, H, W, 2)."""
+    B = x.shape[0]
+    ch = c_out * (2 if mode else 1)
+    assert g.stride(2) == 1 and x.stride(2) == 1 and g.dtype == x.dtype
+    dv = torch.empty((B, ch, H * W), dtype=x.dtype, device=x.device)
+    dw = torch.zeros((ch, 9), dtype=torch.float32, device=x.device)
+    dbias = torch.zeros(ch, dtype=torch.float32, device=x.device) if bias is not None else None
+    a = _lib.DwconvBwdArgs(_ptr(x), _ptr(w9), _ptr(bias), _ptr(g), _ptr(dv), _ptr(dw), _ptr(dbias), B, c_out, H, W, mode,
+                           x.stride(0), x.stride(1), g.stride(0), g.stride(1), dv.stride(0), dv.stride(1), _DT[x.dtype])
+    _run("vmb_dwconv3x3_bwd", a, x, "dwconv_bwd", 0, 2)
+    return dv, dw, dbias
+
+
+def channel_gate_bwd(dyg, y2, gate, mode):
+    """dyg, y2: (B,C,L) contiguous; gate (B,C) fp32 -> (dy2 (B,C,L), dgate (B,C) fp32)."""
+    B, C_, L = y2.shape
+    assert dyg.is_contiguous() and y2.is_contiguous() and gate.is_contiguous() and gate.dtype == torch.float32
+    dy2 = torch.empty_like(y2)
+    dg = torch.empty((B, C_), dtype=torch.float32, device=y2.device)
+    a = _lib.GateBwdArgs(_ptr(dyg), _ptr(y2), _ptr(gate), _ptr(dy2), _ptr(dg), B, C_, L, mode, _DT[y2.dtype])
+    _run("vmb_channel_gate_bwd", a, y2, "gate_bwd")
+    return dy2, dg
