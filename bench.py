@@ -100,11 +100,32 @@ def workload_name(net):
 
 
 def host_threads():
-    """CPU threads this process may use: the scheduler affinity mask (respects cgroup cpusets / taskset), not os.cpu_count()."""
+    """CPU threads for the CPU arm: PHYSICAL cores inside this process's scheduler affinity mask (respects cpusets / taskset),
+    capped by the cgroup CPU quota.  (All 128 SMT threads of the GPU box ran the oracle 100x slower than its 64 cores.)"""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        aff = os.sched_getaffinity(0)
     except AttributeError:
         return os.cpu_count() or 1
+    cores, cur = set(), {}
+    try:
+        for line in open("/proc/cpuinfo"):
+            if ":" in line:
+                k, v = line.split(":", 1)
+                cur[k.strip()] = v.strip()
+            elif cur:
+                if int(cur.get("processor", -1)) in aff:
+                    cores.add((cur.get("physical id"), cur.get("core id")))
+                cur = {}
+    except OSError:
+        pass
+    n = len(cores) if cores else len(aff)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(q) // int(per)))
+    except (OSError, ValueError):
+        pass
+    return max(1, min(n, len(aff)))
 
 
 def bench_input(rank=0):

@@ -9,6 +9,7 @@
 // The 1x1-conv data gradients reuse vmb_pixlin with the transposed weight; the scan gradient is vmb_selective_scan_bwd.
 #include "common.cuh"
 #include "train_params.h"
+#include "dwconv_common.cuh"
 
 namespace vmb {
 
@@ -33,6 +34,21 @@ __device__ __forceinline__ float dgelu_t(float v) {  // Phi(v) + v*phi(v)
     const float cdf = 0.5f * (1.f + erf_t(v * 0.70710678118654752f));
     return fmaf(v * 0.3989422804014327f, ex2(-0.5f * v * v * kLog2e), cdf);
 }
+
+template <typename in_t> struct Pair;
+template <> struct Pair<float> {
+    static __device__ __forceinline__ float2 ld(const float* p) { return *reinterpret_cast<const float2*>(p); }
+    static __device__ __forceinline__ void st(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+};
+template <> struct Pair<__nv_bfloat16> {
+    static __device__ __forceinline__ float2 ld(const __nv_bfloat16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, float2 v) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y); }
+};
+template <> struct Pair<__half> {
+    static __device__ __forceinline__ float2 ld(const __half* p) { return __half22float2(*reinterpret_cast<const __half2*>(p)); }
+    static __device__ __forceinline__ void st(__half* p, float2 v) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(v.x, v.y); }
+};
+
 
 __device__ __forceinline__ float block_sum_256(float v, float* sred) {  // 256 threads; result valid in thread 0
 #pragma unroll
@@ -131,6 +147,17 @@ __global__ void __launch_bounds__(256) ln_bwd_dwdb_kernel(const LnBwdParams p) {
     const in_t* __restrict__ g = reinterpret_cast<const in_t*>(p.g) + (int64_t)b * p.g_bs + (int64_t)c * p.g_cs;
     const float2* __restrict__ st = reinterpret_cast<const float2*>(p.stats) + (int64_t)b * p.L;
     float aw = 0.f, ab = 0.f;
+    if ((p.L & 1) == 0 && ((p.x_bs | p.x_cs | p.g_bs | p.g_cs) & 1) == 0 && (reinterpret_cast<uintptr_t>(p.x) & 7) == 0 &&
+        (reinterpret_cast<uintptr_t>(p.g) & 7) == 0) {
+#pragma unroll 4
+        for (int l = threadIdx.x * 2; l < p.L; l += 512) {
+            const float4 s = *reinterpret_cast<const float4*>(st + l);
+            const float2 gv = Pair<in_t>::ld(g + l), xv = Pair<in_t>::ld(x + l);
+            aw = fmaf(gv.x, (p.mode == 1 ? xv.x - s.x : xv.x) * s.y, aw);
+            aw = fmaf(gv.y, (p.mode == 1 ? xv.y - s.z : xv.y) * s.w, aw);
+            ab += gv.x + gv.y;
+        }
+    } else
     for (int l = threadIdx.x; l < p.L; l += 256) {
         const float2 s = st[l];
         const float gv = to_f32<in_t>(g[l]), xv = to_f32<in_t>(x[l]);
@@ -211,24 +238,179 @@ __global__ void __launch_bounds__(256) merge_bwd_dwdb_kernel(const MergeBwdParam
     }
 }
 
-// ------------------------------------------------------------------------------------------ depthwise 3x3 backward
-template <typename in_t>
-__device__ __forceinline__ float dw_at_t(const in_t* __restrict__ xc, const float* __restrict__ w9, int h, int w, int H, int W) {
-    float acc = 0.f;
+
+// ------------------------------------------------------------------------------------------ channel-split pixel kernels (fast path)
+// The per-pixel LayerNorm kernels above walk all C channels in one thread (3 dependent passes, 16 K threads at 4 x 64x64: latency
+// bound).  Fast path for even L and 4-byte aligned rows: a CTA of 256 threads owns 64 pixels (32 pairs, one 32-bit / 64-bit load
+// per channel) x 8 channel slices; the per-pixel sums of the slices meet in shared memory.
+constexpr int PX_PAIRS = 32, PX_Q = 8;
+
+// sum of `v` over the PX_Q channel slices of one pixel pair; every thread of the pair gets the total
+__device__ __forceinline__ float2 slice_sum(float2 v, float2 (*sm)[PX_PAIRS], int pp, int q) {
+    __syncthreads();
+    sm[q][pp] = v;
+    __syncthreads();
+    float2 t = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-        const int hh = h + dy;
-        if (hh < 0 || hh >= H) continue;
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-            const int ww = w + dx;
-            if (ww < 0 || ww >= W) continue;
-            acc = fmaf(w9[(dy + 1) * 3 + dx + 1], to_f32<in_t>(xc[hh * W + ww]), acc);
-        }
+    for (int i = 0; i < PX_Q; ++i) {
+        t.x += sm[i][pp].x;
+        t.y += sm[i][pp].y;
     }
-    return acc;
+    return t;
 }
 
+template <typename in_t>
+__global__ void __launch_bounds__(256) ln_fwd_px_kernel(const LnFwdParams p) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float2 sm[PX_Q][PX_PAIRS];
+    const int pp = threadIdx.x % PX_PAIRS, q = threadIdx.x / PX_PAIRS, b = blockIdx.y;
+    const int l = min((blockIdx.x * PX_PAIRS + pp) * 2, p.L - 2);  // tail CTAs redo the last pair (idempotent)
+    const int c0 = q * p.C / PX_Q, c1 = (q + 1) * p.C / PX_Q;
+    const in_t* __restrict__ x = reinterpret_cast<const in_t*>(p.x) + (int64_t)b * p.x_bs + l;
+    float2 s = make_float2(0.f, 0.f);
+    for (int c = c0; c < c1; ++c) {
+        const float2 v = Pair<in_t>::ld(x + (int64_t)c * p.x_cs);
+        s.x += v.x; s.y += v.y;
+    }
+    s = slice_sum(s, sm, pp, q);
+    const float2 mu = make_float2(s.x / p.C, s.y / p.C);
+    float2 v2 = make_float2(0.f, 0.f);
+    for (int c = c0; c < c1; ++c) {
+        const float2 v = Pair<in_t>::ld(x + (int64_t)c * p.x_cs);
+        v2.x = fmaf(v.x - mu.x, v.x - mu.x, v2.x);
+        v2.y = fmaf(v.y - mu.y, v.y - mu.y, v2.y);
+    }
+    v2 = slice_sum(v2, sm, pp, q);
+    const float2 rstd = make_float2(rsqrtf(v2.x / p.C + 1e-5f), rsqrtf(v2.y / p.C + 1e-5f));
+    if (p.stats && q == 0) {
+        float* st = p.stats + ((int64_t)b * p.L + l) * 2;
+        *reinterpret_cast<float4*>(st) = make_float4(mu.x, rstd.x, mu.y, rstd.y);
+    }
+    if (!p.y) return;
+    in_t* __restrict__ y = reinterpret_cast<in_t*>(p.y) + (int64_t)b * p.y_bs + l;
+    for (int c = c0; c < c1; ++c) {
+        const float2 v = Pair<in_t>::ld(x + (int64_t)c * p.x_cs);
+        const float w = p.w[c];
+        float2 o;
+        if (p.mode == 1) {
+            const float bb = p.b[c];
+            o = make_float2(fmaf((v.x - mu.x) * rstd.x, w, bb), fmaf((v.y - mu.y) * rstd.y, w, bb));
+        } else {
+            o = make_float2(v.x * rstd.x * w, v.y * rstd.y * w);
+        }
+        Pair<in_t>::st(y + (int64_t)c * p.y_cs, o);
+    }
+}
+
+template <typename in_t>
+__global__ void __launch_bounds__(256) ln_bwd_dx_px_kernel(const LnBwdParams p) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float2 sm[PX_Q][PX_PAIRS];
+    const int pp = threadIdx.x % PX_PAIRS, q = threadIdx.x / PX_PAIRS, b = blockIdx.y;
+    const int l = min((blockIdx.x * PX_PAIRS + pp) * 2, p.L - 2);
+    const int c0 = q * p.C / PX_Q, c1 = (q + 1) * p.C / PX_Q;
+    const in_t* __restrict__ x = reinterpret_cast<const in_t*>(p.x) + (int64_t)b * p.x_bs + l;
+    const in_t* __restrict__ g = reinterpret_cast<const in_t*>(p.g) + (int64_t)b * p.g_bs + l;
+    float2 s = make_float2(0.f, 0.f);
+    for (int c = c0; c < c1; ++c) {
+        const float2 v = Pair<in_t>::ld(x + (int64_t)c * p.x_cs);
+        s.x += v.x; s.y += v.y;
+    }
+    s = slice_sum(s, sm, pp, q);
+    const float2 mu = make_float2(s.x / p.C, s.y / p.C);
+    float2 vv = make_float2(0.f, 0.f), s1 = vv, s2 = vv;
+    for (int c = c0; c < c1; ++c) {
+        const float2 v = Pair<in_t>::ld(x + (int64_t)c * p.x_cs);
+        const float2 gv = Pair<in_t>::ld(g + (int64_t)c * p.g_cs);
+        const float w = p.w[c];
+        const float dx_ = v.x - mu.x, dy_ = v.y - mu.y;
+        vv.x = fmaf(dx_, dx_, vv.x); vv.y = fmaf(dy_, dy_, vv.y);
+        s1.x = fmaf(gv.x, w, s1.x); s1.y = fmaf(gv.y, w, s1.y);
+        s2.x = fmaf(gv.x * w, p.mode == 1 ? dx_ : v.x, s2.x);
+        s2.y = fmaf(gv.y * w, p.mode == 1 ? dy_ : v.y, s2.y);
+    }
+    vv = slice_sum(vv, sm, pp, q);
+    s1 = slice_sum(s1, sm, pp, q);
+    s2 = slice_sum(s2, sm, pp, q);
+    const float2 rstd = make_float2(rsqrtf(vv.x / p.C + 1e-5f), rsqrtf(vv.y / p.C + 1e-5f));
+    if (q == 0) {
+        float* st = p.stats + ((int64_t)b * p.L + l) * 2;
+        *reinterpret_cast<float4*>(st) = make_float4(mu.x, rstd.x, mu.y, rstd.y);
+    }
+    const float invC = 1.f / p.C;
+    const float2 k1 = make_float2(s1.x * invC, s1.y * invC);
+    const float2 k2 = make_float2(s2.x * invC * rstd.x * rstd.x, s2.y * invC * rstd.y * rstd.y);
+    const in_t* __restrict__ a = p.add ? reinterpret_cast<const in_t*>(p.add) + (int64_t)b * p.a_bs + l : nullptr;
+    in_t* __restrict__ dx = reinterpret_cast<in_t*>(p.dx) + (int64_t)b * p.dx_bs + l;
+    for (int c = c0; c < c1; ++c) {
+        const float2 v = Pair<in_t>::ld(x + (int64_t)c * p.x_cs);
+        const float2 gv = Pair<in_t>::ld(g + (int64_t)c * p.g_cs);
+        const float w = p.w[c];
+        float2 o;
+        if (p.mode == 1) {
+            o.x = rstd.x * (gv.x * w - k1.x - (v.x - mu.x) * k2.x);
+            o.y = rstd.y * (gv.y * w - k1.y - (v.y - mu.y) * k2.y);
+        } else {
+            o.x = rstd.x * (gv.x * w - (v.x - mu.x) * k2.x);
+            o.y = rstd.y * (gv.y * w - (v.y - mu.y) * k2.y);
+        }
+        if (a) {
+            const float2 av = Pair<in_t>::ld(a + (int64_t)c * p.a_cs);
+            o.x += av.x; o.y += av.y;
+        }
+        Pair<in_t>::st(dx + (int64_t)c * p.dx_cs, o);
+    }
+}
+
+template <typename in_t>
+__global__ void __launch_bounds__(256) merge_bwd_dx_px_kernel(const MergeBwdParams p) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float2 sm[PX_Q][PX_PAIRS];
+    const int pp = threadIdx.x % PX_PAIRS, q = threadIdx.x / PX_PAIRS, b = blockIdx.y, C = p.C;
+    const int l = min((blockIdx.x * PX_PAIRS + pp) * 2, p.L - 2);
+    const int c0 = q * C / PX_Q, c1 = (q + 1) * C / PX_Q;
+    const float* __restrict__ m = p.merged + (int64_t)b * C * p.L + l;
+    const float4 st = *reinterpret_cast<const float4*>(p.stats + ((int64_t)b * p.L + l) * 2);  // (sum, sumsq) of two pixels
+    const float invC = 1.f / C;
+    const float2 mu = make_float2(st.x * invC, st.z * invC);
+    const float2 rstd = make_float2(rsqrtf(fmaxf(st.y * invC - mu.x * mu.x, 0.f) + 1e-5f), rsqrtf(fmaxf(st.w * invC - mu.y * mu.y, 0.f) + 1e-5f));
+    const in_t* __restrict__ z = reinterpret_cast<const in_t*>(p.z) + (int64_t)b * p.z_bs + l;
+    const in_t* __restrict__ dy2 = reinterpret_cast<const in_t*>(p.dy2) + (int64_t)b * C * p.L + l;
+    const float* __restrict__ dpool = p.dpooled ? p.dpooled + (int64_t)b * C : nullptr;
+    float2 s1 = make_float2(0.f, 0.f), s2 = s1;
+    for (int c = c0; c < c1; ++c) {
+        const float2 t = Pair<in_t>::ld(dy2 + (int64_t)c * p.L);
+        const float2 zv = Pair<in_t>::ld(z + (int64_t)c * p.z_cs);
+        const float2 mv = *reinterpret_cast<const float2*>(m + (int64_t)c * p.L);
+        const float dp = dpool ? dpool[c] : 0.f, w = p.w[c];
+        const float gx = (t.x + dp) * silu_t(zv.x) * w, gy = (t.y + dp) * silu_t(zv.y) * w;
+        s1.x += gx; s1.y += gy;
+        s2.x = fmaf(gx, mv.x - mu.x, s2.x); s2.y = fmaf(gy, mv.y - mu.y, s2.y);
+    }
+    s1 = slice_sum(s1, sm, pp, q);
+    s2 = slice_sum(s2, sm, pp, q);
+    const float2 k1 = make_float2(s1.x * invC, s1.y * invC);
+    const float2 k2 = make_float2(s2.x * invC * rstd.x * rstd.x, s2.y * invC * rstd.y * rstd.y);
+    in_t* __restrict__ dm = reinterpret_cast<in_t*>(p.dm) + (int64_t)b * C * p.L + l;
+    in_t* __restrict__ dz = reinterpret_cast<in_t*>(p.dz) + (int64_t)b * p.dz_bs + l;
+    for (int c = c0; c < c1; ++c) {
+        const float2 t0 = Pair<in_t>::ld(dy2 + (int64_t)c * p.L);
+        const float2 zv = Pair<in_t>::ld(z + (int64_t)c * p.z_cs);
+        const float2 mv = *reinterpret_cast<const float2*>(m + (int64_t)c * p.L);
+        const float dp = dpool ? dpool[c] : 0.f, w = p.w[c], bb = p.b[c];
+        const float2 t = make_float2(t0.x + dp, t0.y + dp);
+        const float2 d = make_float2(mv.x - mu.x, mv.y - mu.y);
+        const float gx = t.x * silu_t(zv.x) * w, gy = t.y * silu_t(zv.y) * w;
+        Pair<in_t>::st(dm + (int64_t)c * p.L, make_float2(rstd.x * (gx - k1.x - d.x * k2.x), rstd.y * (gy - k1.y - d.y * k2.y)));
+        const float nx = fmaf(d.x * rstd.x, w, bb), ny = fmaf(d.y * rstd.y, w, bb);
+        Pair<in_t>::st(dz + (int64_t)c * p.dz_cs, make_float2(t.x * nx * dsilu_t(zv.x), t.y * ny * dsilu_t(zv.y)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ depthwise 3x3 backward
 // gradient w.r.t. the conv OUTPUT before the activation (the conv is recomputed, nothing but its input was saved):
 //   mode 0: v = dw(x[c]) + b;  dv = g * silu'(v)
 //   mode 1: v1 = dw(x[c]) + b[c], v2 = dw(x[c+Co]) + b[c+Co];  dv[c] = g * v2 * gelu'(v1),  dv[c+Co] = g * gelu(v1)
@@ -248,14 +430,40 @@ __global__ void __launch_bounds__(256) dwconv_bwd_pre_kernel(const DwBwdParams p
         w1[i] = p.mode ? p.w[(c + p.Cout) * 9 + i] : 0.f;
     }
     const float b0 = p.bias ? p.bias[c] : 0.f, b1 = (p.bias && p.mode) ? p.bias[c + p.Cout] : 0.f;
+    if (p.vec_ok) {  // 8-pixel strips, 16 B loads / stores
+        constexpr int V = Vec<in_t>::N;
+        for (int i = (blockIdx.x * 256 + threadIdx.x) * 8; i < L; i += gridDim.x * 256 * 8) {
+            const int h = i / p.W, w = i % p.W;
+            float a0[8], a1[8], gv[8], o0[8], o1[8];
+            dw_strip<in_t>(xb + (int64_t)c * p.x_cs, w0, h, w, p.H, p.W, b0, a0);
+#pragma unroll
+            for (int j = 0; j < 8 / V; ++j) load_vec<in_t>(g + i + j * V, gv + j * V, V, true);
+            if (p.mode == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o0[j] = gv[j] * dsilu_t(a0[j]);
+            } else {
+                dw_strip<in_t>(xb + (int64_t)(c + p.Cout) * p.x_cs, w1, h, w, p.H, p.W, b1, a1);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    o0[j] = gv[j] * a1[j] * dgelu_t(a0[j]);
+                    o1[j] = gv[j] * gelu_t(a0[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8 / V; ++j) store_vec<in_t>(dv + (int64_t)(c + p.Cout) * p.dv_cs + i + j * V, o1 + j * V, V, true);
+            }
+#pragma unroll
+            for (int j = 0; j < 8 / V; ++j) store_vec<in_t>(dv + (int64_t)c * p.dv_cs + i + j * V, o0 + j * V, V, true);
+        }
+        return;
+    }
     for (int i = blockIdx.x * 256 + threadIdx.x; i < L; i += gridDim.x * 256) {
         const int h = i / p.W, w = i % p.W;
-        const float v = dw_at_t<in_t>(xb + (int64_t)c * p.x_cs, w0, h, w, p.H, p.W) + b0;
+        const float v = dw_at<in_t>(xb + (int64_t)c * p.x_cs, w0, h, w, p.H, p.W) + b0;
         const float gv = to_f32<in_t>(g[i]);
         if (p.mode == 0) {
             dv[(int64_t)c * p.dv_cs + i] = from_f32<in_t>(gv * dsilu_t(v));
         } else {
-            const float v2 = dw_at_t<in_t>(xb + (int64_t)(c + p.Cout) * p.x_cs, w1, h, w, p.H, p.W) + b1;
+            const float v2 = dw_at<in_t>(xb + (int64_t)(c + p.Cout) * p.x_cs, w1, h, w, p.H, p.W) + b1;
             dv[(int64_t)c * p.dv_cs + i] = from_f32<in_t>(gv * v2 * dgelu_t(v));
             dv[(int64_t)(c + p.Cout) * p.dv_cs + i] = from_f32<in_t>(gv * gelu_t(v));
         }
@@ -275,6 +483,34 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const DwBwdParams p) 
     float acc[10];
 #pragma unroll
     for (int j = 0; j < 10; ++j) acc[j] = 0.f;
+    if (p.vec_ok) {  // 8-pixel strips: three 16 B row loads of x (+2 halo scalars each) against one 16 B load of dv
+        constexpr int V = Vec<in_t>::N;
+        for (int i = threadIdx.x * 8; i < L; i += 256 * 8) {
+            const int h = i / p.W, w0 = i % p.W;
+            float d[8];
+#pragma unroll
+            for (int j = 0; j < 8 / V; ++j) load_vec<in_t>(dv + i + j * V, d + j * V, V, true);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[9] += d[j];
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int hh = h + dy;
+                if (hh < 0 || hh >= p.H) continue;
+                const in_t* __restrict__ row = x + (int64_t)hh * p.W;
+                float v[10];
+                v[0] = w0 > 0 ? to_f32<in_t>(row[w0 - 1]) : 0.f;
+                v[9] = w0 + 8 < p.W ? to_f32<in_t>(row[w0 + 8]) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 8 / V; ++j) load_vec<in_t>(row + w0 + j * V, v + 1 + j * V, V, true);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    acc[(dy + 1) * 3 + 0] = fmaf(d[j], v[j], acc[(dy + 1) * 3 + 0]);
+                    acc[(dy + 1) * 3 + 1] = fmaf(d[j], v[j + 1], acc[(dy + 1) * 3 + 1]);
+                    acc[(dy + 1) * 3 + 2] = fmaf(d[j], v[j + 2], acc[(dy + 1) * 3 + 2]);
+                }
+            }
+        }
+    } else
     for (int i = threadIdx.x; i < L; i += 256) {
         const int h = i / p.W, w = i % p.W;
         const float d = to_f32<in_t>(dv[i]);
@@ -391,8 +627,16 @@ int fused_adam_launch(const AdamParams& p, cudaStream_t stream) {
         default: set_error("unsupported dtype %d", dtype); return VMB_ERR_INVALID;                     \
     }
 
+static inline bool even(int64_t v) { return (v & 1) == 0; }
+static inline bool al8(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7) == 0; }
+
 int ln_fwd_launch(const LnFwdParams& p, int dtype, cudaStream_t stream) {
     VMB_CHECK(p.B <= 65535, "layernorm_fwd: batch > 65535");
+    if (p.L >= 2 && even(p.L) && even(p.x_bs) && even(p.x_cs) && even(p.y_bs) && even(p.y_cs) && al8(p.x) && (!p.y || al8(p.y)) && p.C >= PX_Q) {
+        VMB_DISPATCH(dtype, ln_fwd_px_kernel, dim3((p.L / 2 + PX_PAIRS - 1) / PX_PAIRS, p.B), dim3(256), p);
+        VMB_CUDA(cudaGetLastError());
+        return VMB_OK;
+    }
     VMB_DISPATCH(dtype, ln_fwd_kernel, dim3((p.L + 127) / 128, p.B), dim3(128), p);
     VMB_CUDA(cudaGetLastError());
     return VMB_OK;
@@ -400,6 +644,10 @@ int ln_fwd_launch(const LnFwdParams& p, int dtype, cudaStream_t stream) {
 
 int ln_bwd_launch(const LnBwdParams& p, int dtype, cudaStream_t stream) {
     VMB_CHECK(p.B <= 65535 && p.C <= 65535, "layernorm_bwd: batch / channels > 65535");
+    if (p.L >= 2 && even(p.L) && even(p.x_bs) && even(p.x_cs) && even(p.g_bs) && even(p.g_cs) && even(p.a_bs) && even(p.a_cs) && even(p.dx_bs) &&
+        even(p.dx_cs) && al8(p.x) && al8(p.g) && al8(p.dx) && (!p.add || al8(p.add)) && p.C >= PX_Q) {
+        VMB_DISPATCH(dtype, ln_bwd_dx_px_kernel, dim3((p.L / 2 + PX_PAIRS - 1) / PX_PAIRS, p.B), dim3(256), p);
+    } else
     VMB_DISPATCH(dtype, ln_bwd_dx_kernel, dim3((p.L + 127) / 128, p.B), dim3(128), p);
     if (p.dw) VMB_DISPATCH(dtype, ln_bwd_dwdb_kernel, dim3(p.C, p.B), dim3(256), p);
     VMB_CUDA(cudaGetLastError());
@@ -408,6 +656,10 @@ int ln_bwd_launch(const LnBwdParams& p, int dtype, cudaStream_t stream) {
 
 int merge_bwd_launch(const MergeBwdParams& p, int dtype, cudaStream_t stream) {
     VMB_CHECK(p.B <= 65535 && p.C <= 65535, "merge_bwd: batch / channels > 65535");
+    if (p.L >= 2 && even(p.L) && even(p.z_bs) && even(p.z_cs) && even(p.dz_bs) && even(p.dz_cs) && al8(p.z) && al8(p.dz) && al8(p.dy2) &&
+        al8(p.dm) && (reinterpret_cast<uintptr_t>(p.stats) & 15) == 0 && p.C >= PX_Q) {
+        VMB_DISPATCH(dtype, merge_bwd_dx_px_kernel, dim3((p.L / 2 + PX_PAIRS - 1) / PX_PAIRS, p.B), dim3(256), p);
+    } else
     VMB_DISPATCH(dtype, merge_bwd_dx_kernel, dim3((p.L + 127) / 128, p.B), dim3(128), p);
     VMB_DISPATCH(dtype, merge_bwd_dwdb_kernel, dim3(p.C, p.B), dim3(256), p);
     VMB_CUDA(cudaGetLastError());
@@ -418,7 +670,8 @@ int dwconv_bwd_launch(const DwBwdParams& p, int dtype, cudaStream_t stream) {
     const int L = p.H * p.W;
     const int chans = p.mode ? 2 * p.Cout : p.Cout;
     VMB_CHECK((long)p.B * chans <= 65535, "dwconv_bwd: batch * channels > 65535");
-    VMB_DISPATCH(dtype, dwconv_bwd_pre_kernel, dim3((L + 255) / 256, p.B * p.Cout), dim3(256), p);
+    const int per = p.vec_ok ? 8 : 1;
+    VMB_DISPATCH(dtype, dwconv_bwd_pre_kernel, dim3((L / per + 255) / 256 > 0 ? (L / per + 255) / 256 : 1, p.B * p.Cout), dim3(256), p);
     VMB_CUDA(cudaGetLastError());
     return VMB_OK;
 }
@@ -473,7 +726,12 @@ extern "C" int vmb_dwconv3x3_bwd(const vmb_dwconv_bwd_args* a, void* stream) {
     VMB_CHECK(a && a->x && a->w && a->g && a->dv, "dwconv_bwd: null pointer");
     VMB_CHECK(tdt_ok(a->dtype) && (a->mode == 0 || a->mode == 1) && a->batch > 0 && a->c_out > 0 && a->H > 0 && a->W > 0, "dwconv_bwd: bad arguments");
     DwBwdParams p{a->x, a->w, a->bias, a->g, a->dv, a->dw, a->dbias, a->batch, a->c_out, a->H, a->W, a->mode,
-                  a->x_bs, a->x_cs, a->g_bs, a->g_cs, a->dv_bs, a->dv_cs};
+                  a->x_bs, a->x_cs, a->g_bs, a->g_cs, a->dv_bs, a->dv_cs, false};
+    {
+        auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+        p.vec_ok = a->W % 8 == 0 && al16(a->x) && al16(a->g) && al16(a->dv) && a->x_bs % 8 == 0 && a->x_cs % 8 == 0 && a->g_bs % 8 == 0 &&
+                   a->g_cs % 8 == 0 && a->dv_bs % 8 == 0 && a->dv_cs % 8 == 0;
+    }
     int rc = dwconv_bwd_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
     if (rc != VMB_OK || !a->dw) return rc;
     return dwconv_wgrad_launch(p, a->dtype, static_cast<cudaStream_t>(stream));

@@ -24,6 +24,7 @@ struct DwBwdParams {
     const void* x; const float* w; const float* bias; const void* g; void* dv; float* dwgt; float* dbias;
     int B, Cout, H, W, mode;
     int64_t x_bs, x_cs, g_bs, g_cs, dv_bs, dv_cs;
+    bool vec_ok;  // W % 8 == 0, 16 B aligned rows: 8-pixel strips
 };
 struct GateBwdParams {
     const void* dyg; const void* y2; const float* gate; void* dy2; float* dgate;

@@ -49,13 +49,13 @@ class _Front(torch.autograd.Function):
             N, R = A_logs.shape[1], dt_w.shape[2]
             ln_mode = 1 if n1b is not None else 2
             x3 = x.contiguous().view(B, C, L)
-            Win, _ = _wt(w_in.view(2 * C, C), dt_)
+            Win, WinT = _wt(w_in.view(2 * C, C), dt_)
             xz = ops.pixlin(x3, Win, _f32(b_in), ln=(ln_mode, _f32(n1w), _f32(n1b)))  # (B,2C,L): [x_pre | z_pre], no activation
             cw9 = _f32(cw.view(C, 9))
             xc = ops.dwconv3x3(xz[:, :C], cw9, _f32(cb), C, H, W, 0)
             xw, dtw = x_proj_w.detach().float(), dt_w.detach().float()
             big = torch.cat([torch.cat([dtw[k] @ xw[k, :R], xw[k, R:]], 0) for k in range(4)], 0)  # (4(C+2N), C)
-            Wbig, _ = _wt(big, dt_)
+            Wbig, WbigT = _wt(big, dt_)
             dbl4 = ops.pixlin(xc, Wbig).view(B, 4, C + 2 * N, L)   # delta, B, C of the four directions, pixel order
             xs = ops.cross_scan([xc] * 4, C, H, W)
             dts = ops.cross_scan([dbl4[:, k, :C] for k in range(4)], C, H, W)
@@ -65,14 +65,16 @@ class _Front(torch.autograd.Function):
                                               _f32(dt_b.reshape(-1)), True, need_ckpt=True)
             y2, pooled, ws = ops.merge_norm_gate(ys.view(B, 4, C, L), xz[:, C:], _f32(on_w), _f32(on_b), C, H, W,
                                                  z_preact=True, return_ws=True)
-            ctx.save_for_backward(x3, xz, xc, xs, dts, bc, ckpt, ws, A, n1w, n1b, w_in, cw, cb, x_proj_w, dt_w, dt_b, Ds, on_w, on_b)
+            ctx.save_for_backward(x3, xz, xc, xs, dts, bc, ckpt, ws, A, n1w, n1b, w_in, cw, cb, x_proj_w, dt_w, dt_b, Ds, on_w, on_b,
+                                  WinT, WbigT)
             ctx.geom = (B, C, H, W, N, R, ln_mode)
         return y2.view(B, C, H, W), pooled
 
     @staticmethod
     def backward(ctx, dy2, dpooled):
         with torch.autocast("cuda", enabled=False):
-            x3, xz, xc, xs, dts, bc, ckpt, ws, A, n1w, n1b, w_in, cw, cb, x_proj_w, dt_w, dt_b, Ds, on_w, on_b = ctx.saved_tensors
+            (x3, xz, xc, xs, dts, bc, ckpt, ws, A, n1w, n1b, w_in, cw, cb, x_proj_w, dt_w, dt_b, Ds, on_w, on_b,
+             WinT, WbigT) = ctx.saved_tensors
             B, C, H, W, N, R, ln_mode = ctx.geom
             L, dt_ = H * W, x3.dtype
             dy2 = dy2.to(dt_).contiguous().view(B, C, L)
@@ -91,8 +93,6 @@ class _Front(torch.autograd.Function):
             ops.cross_scan([dC[:, k] for k in range(4)], N, W, H, out=ddbl[:, :, C + N:])
             ddbl = ddbl.view(B, 4 * (C + 2 * N), L)
             xw, dtw = x_proj_w.detach().float(), dt_w.detach().float()
-            big = torch.cat([torch.cat([dtw[k] @ xw[k, :R], xw[k, R:]], 0) for k in range(4)], 0)
-            _, WbigT = _wt(big, dt_)
             dxc = ops.pixlin(ddbl, WbigT)
             dxc = (dxc.float() + dxc4.float().sum(1)).to(dt_)
             dbig = _wgrad(ddbl, xc).view(4, C + 2 * N, C)
@@ -105,7 +105,6 @@ class _Front(torch.autograd.Function):
             dv, d_cw, d_cb = ops.dwconv3x3_bwd(xz[:, :C], cw9, _f32(cb), dxc, C, H, W, 0)
             ops.dwconv3x3(dv, cw9.flip(-1).contiguous(), None, C, H, W, 2, out=dxz[:, :C])
             # in_conv + norm1
-            _, WinT = _wt(w_in.view(2 * C, C), dt_)
             dxn = ops.pixlin(dxz, WinT)
             xn = ops.layernorm_fwd(x3, ln_mode, _f32(n1w), _f32(n1b))
             d_win = _wgrad(dxz, xn).view_as(w_in)
@@ -126,43 +125,43 @@ class _Tail(torch.autograd.Function):
             ln_mode = 1 if n2b is not None else 2
             x3, y23 = x.contiguous().view(B, C, L), y2.contiguous().view(B, C, L)
             cg = c.detach().float().contiguous()
-            Wout, _ = _wt(w_out.view(C, C), dt_)
+            Wout, WoutT = _wt(w_out.view(C, C), dt_)
             x1 = ops.pixlin(y23, Wout, _f32(b_out), residual=x3, gate=cg, gate_mode=gate_mode)
-            Wpin, _ = _wt(w_pin.view(2 * h, C), dt_)
+            Wpin, WpinT = _wt(w_pin.view(2 * h, C), dt_)
             t = ops.pixlin(x1, Wpin, _f32(b_pin), ln=(ln_mode, _f32(n2w), _f32(n2b)))
             fdw9 = _f32(fdw.view(2 * h, 9))
             gg = ops.dwconv3x3(t, fdw9, _f32(fdwb), h, H, W, 1)
-            Wpout, _ = _wt(w_pout.view(C, h), dt_)
+            Wpout, WpoutT = _wt(w_pout.view(C, h), dt_)
             out = ops.pixlin(gg, Wpout, _f32(b_pout), residual=x1)
-            ctx.save_for_backward(y23, cg, x1, t, gg, w_out, b_out, n2w, n2b, w_pin, b_pin, fdw, fdwb, w_pout, b_pout)
+            ctx.save_for_backward(y23, cg, x1, t, gg, w_out, b_out, n2w, n2b, w_pin, b_pin, fdw, fdwb, w_pout, b_pout,
+                                  WoutT, WpinT, WpoutT)
             ctx.geom = (B, C, H, W, h, ln_mode, gate_mode)
         return out.view(B, C, H, W)
 
     @staticmethod
     def backward(ctx, dout):
         with torch.autocast("cuda", enabled=False):
-            y23, cg, x1, t, gg, w_out, b_out, n2w, n2b, w_pin, b_pin, fdw, fdwb, w_pout, b_pout = ctx.saved_tensors
+            (y23, cg, x1, t, gg, w_out, b_out, n2w, n2b, w_pin, b_pin, fdw, fdwb, w_pout, b_pout,
+             WoutT, WpinT, WpoutT) = ctx.saved_tensors
             B, C, H, W, h, ln_mode, gate_mode = ctx.geom
             L, dt_ = H * W, x1.dtype
             dout3 = dout.to(dt_).contiguous().view(B, C, L)
             # project_out
-            _, WpoutT = _wt(w_pout.view(C, h), dt_)
             dgg = ops.pixlin(dout3, WpoutT)
-            d_wpout = _wgrad(dout3, gg).view_as(w_pout)
+            # (h, C) product then transposed: an output row of h = int(2.66 C) bf16 elements is not 16 B aligned (slow GEMM path)
+            d_wpout = _wgrad(gg, dout3).t().reshape(w_pout.shape)
             d_bpout = dout3.float().sum((0, 2)) if b_pout is not None else None
             # depthwise conv + GELU gate
             fdw9 = _f32(fdw.view(2 * h, 9))
             dv, d_fdw, d_fdwb = ops.dwconv3x3_bwd(t, fdw9, _f32(fdwb), dgg, h, H, W, 1)
             dt = ops.dwconv3x3(dv, fdw9.flip(-1).contiguous(), None, 2 * h, H, W, 2)
             # project_in + norm2 (+ the residual branch of the EFFN)
-            _, WpinT = _wt(w_pin.view(2 * h, C), dt_)
             dx1n = ops.pixlin(dt, WpinT)
             x1n = ops.layernorm_fwd(x1, ln_mode, _f32(n2w), _f32(n2b))
             d_wpin = _wgrad(dt, x1n).view_as(w_pin)
             d_bpin = dt.float().sum((0, 2)) if b_pin is not None else None
             dx1, d_n2w, d_n2b = ops.layernorm_bwd(x1, dx1n, ln_mode, _f32(n2w), add=dout3)
             # out_conv with the channel gate in front, residual behind
-            _, WoutT = _wt(w_out.view(C, C), dt_)
             dyg = ops.pixlin(dx1, WoutT)
             dy2, dc = ops.channel_gate_bwd(dyg, y23, cg, gate_mode)
             wb = torch.bmm(dx1, y23.transpose(1, 2)).float()  # (B, C_out, C_in)
