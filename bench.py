@@ -88,7 +88,21 @@ def build_net(kind):
     torch.manual_seed(0)
     if kind == "light":
         return archs.MambaSISR6()  # class default [6,2,2,1] + 6 refinement, 10.5 M params
+    if kind == "derain":  # BASELINE configs[3]: Deraining/Options/Deraining_mamber33.yml:53-63
+        return archs.Mamber32(num_blocks=[3, 5, 7, 9], num_refinement_blocks=2)
+    if kind == "realsr":  # BASELINE configs[4]: RealSR/options/mambaSR11_x4.yml:82-92 (class default [6,2,2,1] + 6)
+        return archs.MambaRealSR11()
     return archs.MambaSISR6(num_blocks=[15, 1, 1, 1], num_refinement_blocks=15)  # options/MambaSISR15_x4.yml
+
+
+# --config N (1-based index into BASELINE.json configs): net, images per GPU, LQ size, oracle kind, metric, workload
+CONFIGS = {
+    2: dict(net=None, B=8, hw=64, kind="sisr", metric=None, workload=None),
+    4: dict(net="derain", B=4, hw=256, kind="mamber32", metric="deraining images/sec (256x256, bf16)",
+            workload="Deraining Mamber32 [3,5,7,9]+2 (28.7M params) inference, B=4 x 3x256x256 per GPU (level-1 scans: L = 65 536)"),
+    5: dict(net="realsr", B=2, hw=128, kind="realsr", metric="RealSR x4 images/sec (128x128 LQ, bf16)",
+            workload="MambaRealSR11 [6,2,2,1]+6 (10.5M params) SRx4 inference, B=2 x 3x128x128 LQ per GPU (16 images over 8 GPUs)"),
+}
 
 
 METRIC = "SRx4 images/sec (64x64 LQ, bf16)"  # BASELINE.json's metric; both arms print this exact string
@@ -198,11 +212,16 @@ def run_infer(args):
     rank, local, world = env_rank()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    B = B_PER_GPU_INFER
+    cfg = CONFIGS[args.config]
+    B, H, W = cfg["B"], cfg["hw"], cfg["hw"]
+    net_kind = cfg["net"] or args.net
     chains = int(os.environ.get("VMB_CHAINS", "1"))
     lowres = int(os.environ.get("VMB_LOWRES_CHAINS", "1"))
-    eng = InferenceEngine(build_net(args.net), B, H, W, dtype=torch.bfloat16, device=dev, chains=chains, lowres_chains=lowres)
-    x_host = bench_input(rank).to(torch.bfloat16).pin_memory()
+    eng = InferenceEngine(build_net(net_kind), B, H, W, dtype=torch.bfloat16, device=dev, chains=chains, lowres_chains=lowres)
+    if args.config == 2:
+        x_host = bench_input(rank).to(torch.bfloat16).pin_memory()
+    else:
+        x_host = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(1234 + rank)).to(torch.bfloat16).pin_memory()
     eng.x_dev.copy_(x_host)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     K, Wm = args.steps, max(args.warmup, 3)
@@ -243,7 +262,7 @@ def run_infer(args):
     y_bench = eng.run(x_host).float().clone()  # result of the benchmarked engine: sanity / parity check below
     if not bool(torch.isfinite(y_bench).all()):
         raise SystemExit("bench.py: the benchmarked forward produced non-finite values")
-    eager = InferenceEngine(build_net(args.net), B, H, W, dtype=torch.bfloat16, device=dev, use_graph=False)
+    eager = InferenceEngine(build_net(net_kind), B, H, W, dtype=torch.bfloat16, device=dev, use_graph=False)
     eager.x_dev.copy_(x_host)
     eager.step_device()
     torch.cuda.synchronize(dev)
@@ -263,11 +282,11 @@ def run_infer(args):
     ms_per_step = total_ms / K
     value = world * B * K / (total_ms * 1e-3)
     out = {
-        "metric": METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": world,
+        "metric": cfg["metric"] or METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": world,
         "steps": K, "warmup": Wm, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "lq_mpix_per_s": round(value * H * W / 1e6, 3),
-        "config": {"workload": workload_name(args.net),
+        "config": {"workload": cfg["workload"] or workload_name(args.net),
                    "global_batch": world * B, "parallelism": f"batch-sharded x{world}, no collective",
                    "l2": "256 MiB memset between timed steps", "graph": f"CUDA graph replay, {chains} whole-net sub-batch chains, levels below full resolution on {lowres} parallel sub-batch branches",
                    "path": f"fused OSS kernels ({eng.launches_per_step} launches of this library per step)" if eng.launches_per_step else "compose"},
@@ -275,7 +294,7 @@ def run_infer(args):
                 "h2d_bytes_per_step": int(x_host.numel() * x_host.element_size()),
                 "d2h_bytes_per_step": int(y.numel() * y.element_size())},
         "gpu_launches": int(eng.launches_per_step * K),
-        "roofline": {"kernel": "scan_fwd_kernel (largest scan of the step: u (8,384,4096) bf16)", "bound": "hbm",
+        "roofline": {"kernel": f"scan_fwd_tma_kernel (largest scan of the step, {top_b / 1e6:.1f} MB of operands; config 2: u (8,384,4096) bf16)", "bound": "hbm",
                      "achieved": round(ach, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": round(ach / peak, 4),
                      # dram__bytes_* of this launch are not measurable outside ncu: null here, the committed capture is cited
@@ -283,11 +302,11 @@ def run_infer(args):
                      "algorithmic_bytes_per_launch": int(top_b),
                      "all_scans_per_step": {"launches": len(big) // 3, "GB": round(tot_b / 3 / 1e9, 4),
                                             "ms": round(tot_ms / 3, 4), "share_of_step": round(tot_ms / 3 / ms_per_step, 3)},
-                     "note": "issue/MUFU-bound, not HBM-bound at bf16 I/O (SURVEY.md 7.3): XU pipe 45 %, issue slots 52 % (ncu)"},
+                     "note": "not HBM-bound at bf16 I/O: the MUFU (ex2), LDS and SHFL instructions of a warp queue on one path (tools/microbench.cu, profiles/scan_fwd_r2.md)"},
         "clocks": clocks,
     }
     if rank == 0:
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.config == 2:
             ips, mean, y_ref = cpu_oracle_images_per_s(steps=2, warmup=1, x=x_host[:1], kind=args.net)
             out["cpu_baseline"] = {"value": round(ips, 4), "unit": "images/s", "cores": torch.get_num_threads(),
                                    "host_cores": os.cpu_count(), "kind": "port",
@@ -328,6 +347,9 @@ def main():
                          "[15,1,1,1]+15 (SURVEY.md 8d asks for both)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step sub-record of the default run")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
+                    help="1-based index into BASELINE.json configs: 2 = VmambaIR-light SRx4 inference (default, the metric's config), "
+                         "4 = deraining 4 x 3x256x256, 5 = RealSR 2 x 3x128x128 per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -343,7 +365,7 @@ def main():
             out = run_train(args, build_net, ClockSampler, env_rank, dist_max, barrier, peaks)
         else:
             out = run_infer(args)
-            if not args.no_train:
+            if not args.no_train and args.config == 2:
                 out["train"] = train_record(args)
         if rank == 0:
             print(json.dumps(out), flush=True)

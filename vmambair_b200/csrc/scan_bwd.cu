@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(32, 8) scan_bwd_kernel(const ScanBwdParams p) 
                         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                     }
                     const int l = c0 + cell;
-                    if (l < L && n0 < N) red_add_f32x4(scratch + (int64_t)(n0 / 2) * L + l, acc);
+                    if (l < L && n0 < N && !p.debug_nored) red_add_f32x4(scratch + (int64_t)(n0 / 2) * L + l, acc);
                 }
                 __syncwarp();
             }
@@ -366,7 +366,9 @@ static int pick_rb_bwd(const ScanBwdParams& p) {
 }
 
 template <typename in_t>
-static int launch_t(const ScanBwdParams& p, cudaStream_t stream) {
+static int launch_t(const ScanBwdParams& p_in, cudaStream_t stream) {
+    ScanBwdParams p = p_in;
+    if (const char* e = getenv("VMB_BWD_NORED")) p.debug_nored = atoi(e);
     const size_t scratch_bytes = sizeof(float4) * (size_t)p.batch * p.G * (p.npad / 2) * p.L;
     VMB_CUDA(cudaMemsetAsync(p.dBC, 0, scratch_bytes, stream));
     int rc;

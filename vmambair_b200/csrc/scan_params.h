@@ -42,6 +42,7 @@ struct ScanBwdParams {
     int64_t B_bs, B_gs, B_ns, C_bs, C_gs, C_ns;
     int softplus;
     bool vec_ok;
+    int debug_nored;  // profiling only (VMB_BWD_NORED=1): skip the dB/dC global reductions
 };
 
 int scan_fwd_launch(const ScanFwdParams& p, int dtype, cudaStream_t stream);
