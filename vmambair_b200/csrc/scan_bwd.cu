@@ -365,6 +365,11 @@ static int pick_rb_bwd(const ScanBwdParams& p) {
     return rb;
 }
 
+template <typename in_t> struct DtOf;
+template <> struct DtOf<float> { static constexpr int v = VMB_F32; };
+template <> struct DtOf<__nv_bfloat16> { static constexpr int v = VMB_BF16; };
+template <> struct DtOf<__half> { static constexpr int v = VMB_F16; };
+
 template <typename in_t>
 static int launch_t(const ScanBwdParams& p_in, cudaStream_t stream) {
     ScanBwdParams p = p_in;
@@ -372,6 +377,10 @@ static int launch_t(const ScanBwdParams& p_in, cudaStream_t stream) {
     const size_t scratch_bytes = sizeof(float4) * (size_t)p.batch * p.G * (p.npad / 2) * p.L;
     VMB_CUDA(cudaMemsetAsync(p.dBC, 0, scratch_bytes, stream));
     int rc;
+    int trb, tss;
+    if (scan_bwd_tma_pick(p, DtOf<in_t>::v, trb, tss)) {  // fast path: TMA-staged 4-warp CTAs (scan_bwd_tma.cu)
+        rc = scan_bwd_tma_launch(p, DtOf<in_t>::v, trb, tss, stream);
+    } else
     switch (pick_rb_bwd(p)) {
         case 8: rc = launch_cfg<in_t, 8>(p, stream); break;
         case 4: rc = launch_cfg<in_t, 4>(p, stream); break;

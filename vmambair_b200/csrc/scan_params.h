@@ -49,5 +49,7 @@ int scan_fwd_launch(const ScanFwdParams& p, int dtype, cudaStream_t stream);
 bool scan_fwd_tma_pick(const ScanFwdParams& p, int& rb, int& ss);
 int scan_fwd_tma_launch(const ScanFwdParams& p, int dtype, int rb, int ss, cudaStream_t stream);
 int scan_bwd_launch(const ScanBwdParams& p, int dtype, cudaStream_t stream);
+bool scan_bwd_tma_pick(const ScanBwdParams& p, int dtype, int& rb, int& ss);
+int scan_bwd_tma_launch(const ScanBwdParams& p, int dtype, int rb, int ss, cudaStream_t stream);
 
 }  // namespace vmb
