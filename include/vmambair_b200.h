@@ -241,6 +241,19 @@ typedef struct {
 } vmb_gate_bwd_args;
 int vmb_channel_gate_bwd(const vmb_gate_bwd_args* a, void* stream);
 
+/* weight gradient of a 1x1 conv: out[m][k] += sum_{b,p} dy[b][m][p] * x[b][k][p]  (out fp32 (M,K), accumulated: the caller zero-fills;
+ * per_batch != 0: out is (B,M,K) and batches are not summed -- the channel gate in front of out_conv scales them per image).
+ * dy (B,M,L), x (B,K,L): bf16 / fp16 views with 16 B aligned, pixel-contiguous rows.  mma.sync tensor-core kernel, split over
+ * pixels.  (fp32 activations: use the library GEMM.) */
+typedef struct {
+    const void* dy; const void* x; float* out;
+    int batch, M, K, L;
+    int64_t dy_bs, dy_cs, x_bs, x_cs;
+    int per_batch;
+    int dtype;
+} vmb_wgrad_args;
+int vmb_pixlin_wgrad(const vmb_wgrad_args* a, void* stream);
+
 /* Fused Adam / AdamW step + gradient clipping + EMA over FLAT fp32 buffers of n elements (optimizer_g.step(), clip_grad_norm_,
  * model_ema(): SRGAN/VmambaIR/models/MambaSISR_model.py:141-147, Deraining/basicsr/models/image_restoration_model.py:165-173,
  * Deraining/basicsr/models/base_model.py:54-62).  grad is first multiplied by grad_scale (1/world after the all-reduce) and, when

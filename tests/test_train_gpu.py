@@ -88,3 +88,20 @@ def test_block_fused_training_bf16_close_to_fp32():
             continue
         rel = float((g16[n] - g32[n]).norm() / g32[n].norm().clamp_min(1e-8))
         assert rel < 0.08, (n, rel)
+
+
+@pytest.mark.parametrize("B,M,K,L", [(4, 510, 96, 4096), (2, 96, 255, 1024), (1, 35, 48, 520), (3, 192, 96, 256)])
+@pytest.mark.parametrize("per_batch", [False, True])
+def test_pixlin_wgrad_matches_fp32_contraction(B, M, K, L, per_batch):
+    """dW[m,k] = sum_{b,p} dy[b,m,p] x[b,k,p]: the split-pixel mma.sync kernel (bf16 in, fp32 accumulate) vs an fp32 einsum of the
+    same bf16-rounded operands; also through channel-offset views (strided rows)."""
+    from vmambair_b200 import ops
+    torch.manual_seed(B * 7 + M)
+    dy_full = torch.randn(B, M + 8, L, device="cuda").to(torch.bfloat16)
+    dy = dy_full[:, 8:]  # a channel-offset view, like the d z_pre half of dxz
+    x = torch.randn(B, K, L, device="cuda").to(torch.bfloat16)
+    got = ops.pixlin_wgrad(dy, x, per_batch=per_batch)
+    ref = torch.einsum("bmp,bkp->bmk", dy.float(), x.float())
+    ref = ref if per_batch else ref.sum(0)
+    assert got.dtype == torch.float32 and got.shape == ref.shape
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-2 * float(ref.abs().max()) * 1e-2 + 1e-3)

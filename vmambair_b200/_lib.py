@@ -135,6 +135,11 @@ class GateBwdArgs(C.Structure):
                 ("batch", C.c_int), ("C", C.c_int), ("L", C.c_int), ("mode", C.c_int), ("dtype", C.c_int)]
 
 
+class WgradArgs(C.Structure):
+    _fields_ = [("dy", vp), ("x", vp), ("out", vp), ("batch", C.c_int), ("M", C.c_int), ("K", C.c_int), ("L", C.c_int),
+                ("dy_bs", i64), ("dy_cs", i64), ("x_bs", i64), ("x_cs", i64), ("per_batch", C.c_int), ("dtype", C.c_int)]
+
+
 class AdamArgs(C.Structure):
     _fields_ = [("param", vp), ("grad", vp), ("exp_avg", vp), ("exp_avg_sq", vp), ("ema", vp), ("state", vp),
                 ("n", C.c_long), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
@@ -165,6 +170,7 @@ SYMBOLS = {
     "vmb_dwconv3x3_bwd": (C.c_int, [C.POINTER(DwconvBwdArgs), vp]),
     "vmb_channel_gate_bwd": (C.c_int, [C.POINTER(GateBwdArgs), vp]),
     "vmb_fused_adam": (C.c_int, [C.POINTER(AdamArgs), vp]),
+    "vmb_pixlin_wgrad": (C.c_int, [C.POINTER(WgradArgs), vp]),
 }
 
 

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/vmambair_b200.h"
+
 namespace vmb {
 struct LnFwdParams {
     const void* x; const float* w; const float* b; void* y; float* stats;
@@ -38,6 +40,13 @@ struct AdamParams {
     float grad_scale, max_norm, ema_decay;
     int zero_grad;
 };
+struct WgradParams {
+    const void* dy; const void* x; float* out;
+    int B, M, K, L;
+    int64_t dy_bs, dy_cs, x_bs, x_cs;
+    int splits, per_batch;
+};
+int wgrad_launch(const WgradParams& p, int dtype, cudaStream_t stream);
 int fused_adam_launch(const AdamParams& p, cudaStream_t stream);
 int ln_fwd_launch(const LnFwdParams& p, int dtype, cudaStream_t stream);
 int ln_bwd_launch(const LnBwdParams& p, int dtype, cudaStream_t stream);

@@ -15,8 +15,8 @@ Structure (two autograd Functions with the tiny channel-direction branch between
 Backward kernels: vmb_pixlin with the transposed weight (data gradients of the five 1x1 convs), vmb_selective_scan_bwd,
 vmb_cross_scan (the gathers pi_k and their inverses = pi_k with H and W swapped, bit-exact permutations),
 vmb_merge_norm_gate_bwd, vmb_layernorm_fwd/bwd, vmb_dwconv3x3_bwd + vmb_dwconv3x3 (flipped taps), vmb_channel_gate_bwd.
-The five weight-gradient contractions dW = sum_{b,p} dY X^T are plain GEMMs and go to cuBLAS (torch.bmm); bias gradients are
-row sums.  Activations are saved in the compute dtype (bf16 under autocast), parameters stay fp32 and receive fp32 gradients.
+The five weight-gradient contractions dW = sum_{b,p} dY X^T run vmb_pixlin_wgrad (mma.sync, split over pixels; fp32 parity mode:
+the library GEMM); bias gradients are row sums.  Activations are saved in the compute dtype (bf16 under autocast), parameters stay fp32 and receive fp32 gradients.
 """
 from __future__ import annotations
 
@@ -36,8 +36,8 @@ def _wt(w2d, dtype):
 
 
 def _wgrad(dy, x):
-    """dW[m,k] = sum_{b,p} dy[b,m,p] x[b,k,p]  (fp32 result; plain GEMM -> cuBLAS)"""
-    return torch.bmm(dy, x.transpose(1, 2)).float().sum(0)
+    """dW[m,k] = sum_{b,p} dy[b,m,p] x[b,k,p]  (fp32 result; this library's split-pixel mma kernel for 16-bit activations)"""
+    return ops.pixlin_wgrad(dy, x)
 
 
 class _Front(torch.autograd.Function):
@@ -148,8 +148,7 @@ class _Tail(torch.autograd.Function):
             dout3 = dout.to(dt_).contiguous().view(B, C, L)
             # project_out
             dgg = ops.pixlin(dout3, WpoutT)
-            # (h, C) product then transposed: an output row of h = int(2.66 C) bf16 elements is not 16 B aligned (slow GEMM path)
-            d_wpout = _wgrad(gg, dout3).t().reshape(w_pout.shape)
+            d_wpout = _wgrad(dout3, gg).view_as(w_pout)
             d_bpout = dout3.float().sum((0, 2)) if b_pout is not None else None
             # depthwise conv + GELU gate
             fdw9 = _f32(fdw.view(2 * h, 9))
@@ -164,7 +163,7 @@ class _Tail(torch.autograd.Function):
             # out_conv with the channel gate in front, residual behind
             dyg = ops.pixlin(dx1, WoutT)
             dy2, dc = ops.channel_gate_bwd(dyg, y23, cg, gate_mode)
-            wb = torch.bmm(dx1, y23.transpose(1, 2)).float()  # (B, C_out, C_in)
+            wb = ops.pixlin_wgrad(dx1, y23, per_batch=True)  # (B, C_out, C_in): the channel gate scales it per image
             if gate_mode == 1:
                 d_wout = (wb * (1.0 + cg)[:, None, :]).sum(0)
             else:

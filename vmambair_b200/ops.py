@@ -346,3 +346,21 @@ def channel_gate_bwd(dyg, y2, gate, mode):
     a = _lib.GateBwdArgs(_ptr(dyg), _ptr(y2), _ptr(gate), _ptr(dy2), _ptr(dg), B, C_, L, mode, _DT[y2.dtype])
     _run("vmb_channel_gate_bwd", a, y2, "gate_bwd")
     return dy2, dg
+
+
+def pixlin_wgrad(dy, x, per_batch=False):
+    """dW[m,k] = sum_{b,p} dy[b,m,p] x[b,k,p] -> fp32 (M,K)  (or (B,M,K) without the batch sum).  16-bit activations with 16 B aligned
+    rows run this library's mma.sync split-pixel kernel; fp32 (parity mode) or unaligned rows go to the library GEMM."""
+    B, M, L = dy.shape
+    K = x.shape[1]
+    ok = (dy.dtype in (torch.bfloat16, torch.float16) and x.dtype == dy.dtype and dy.stride(2) == 1 and x.stride(2) == 1
+          and all(s % 8 == 0 for s in (dy.stride(0), dy.stride(1), x.stride(0), x.stride(1)))
+          and dy.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0)
+    if not ok:
+        wb = torch.bmm(dy, x.transpose(1, 2)).float()
+        return wb if per_batch else wb.sum(0)
+    out = torch.zeros((B, M, K) if per_batch else (M, K), dtype=torch.float32, device=dy.device)
+    a = _lib.WgradArgs(_ptr(dy), _ptr(x), _ptr(out), B, M, K, L, dy.stride(0), dy.stride(1), x.stride(0), x.stride(1),
+                       int(per_batch), _DT[dy.dtype])
+    _run("vmb_pixlin_wgrad", a, dy, "wgrad")
+    return out
