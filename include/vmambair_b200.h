@@ -251,8 +251,30 @@ typedef struct {
     int64_t dy_bs, dy_cs, x_bs, x_cs;
     int per_batch;
     int dtype;
+    float* dbias; /* optional (M) fp32, accumulated: dbias[m] += sum_{b,p} dy[b][m][p] (the conv's bias gradient) */
 } vmb_wgrad_args;
 int vmb_pixlin_wgrad(const vmb_wgrad_args* a, void* stream);
+
+/* Per-step weight preparation of one OSS block in ONE launch: every job converts an fp32 parameter into the layout a kernel of
+ * this library consumes.  type 0: (M,K) -> dst (M, ld) in `dtype`, columns >= K zero;  1: (M,K) -> dst (K, ld) = transpose, columns
+ * >= M zero;  2: fold x_proj (src: (4, K+N2, M)) and dt_proj (src2: (4, M, K)) into big (dst: (4(M+N2), ld)) and its transpose
+ * (dst2: (M, ld2)) -- big[k] = [W_dt,k W_x,k[:K] ; W_x,k[K:]], M = C, K = dt_rank, N2 = 2*d_state;  3: dst = -exp(src), fp32 (M,K);
+ * 4: dst = the 9 taps of (M, 9) spatially flipped, fp32. */
+#define VMB_PREP_MAX_JOBS 16
+typedef struct {
+    const float* src; const float* src2; void* dst; void* dst2;
+    int type, M, K, N2, ld, ld2;
+} vmb_prep_job;
+typedef struct {
+    vmb_prep_job jobs[VMB_PREP_MAX_JOBS];
+    int njobs;
+    int dtype;
+} vmb_prep_args;
+int vmb_prep_block_weights(const vmb_prep_args* a, void* stream);
+
+/* out = add + x4[:,0] + x4[:,1] + x4[:,2] + x4[:,3]: x4 (batch, 4, per_dir) contiguous, add / out (batch, per_dir) contiguous
+ * (the four un-permuted direction gradients of the scan input joined with the x_proj data gradient). */
+int vmb_sum4_add(const void* x4, const void* add, void* out, int batch, long per_dir, int dtype, void* stream);
 
 /* Fused Adam / AdamW step + gradient clipping + EMA over FLAT fp32 buffers of n elements (optimizer_g.step(), clip_grad_norm_,
  * model_ema(): SRGAN/VmambaIR/models/MambaSISR_model.py:141-147, Deraining/basicsr/models/image_restoration_model.py:165-173,

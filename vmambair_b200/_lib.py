@@ -137,7 +137,17 @@ class GateBwdArgs(C.Structure):
 
 class WgradArgs(C.Structure):
     _fields_ = [("dy", vp), ("x", vp), ("out", vp), ("batch", C.c_int), ("M", C.c_int), ("K", C.c_int), ("L", C.c_int),
-                ("dy_bs", i64), ("dy_cs", i64), ("x_bs", i64), ("x_cs", i64), ("per_batch", C.c_int), ("dtype", C.c_int)]
+                ("dy_bs", i64), ("dy_cs", i64), ("x_bs", i64), ("x_cs", i64), ("per_batch", C.c_int), ("dtype", C.c_int),
+                ("dbias", vp)]
+
+
+class PrepJob(C.Structure):
+    _fields_ = [("src", vp), ("src2", vp), ("dst", vp), ("dst2", vp), ("type", C.c_int), ("M", C.c_int), ("K", C.c_int),
+                ("N2", C.c_int), ("ld", C.c_int), ("ld2", C.c_int)]
+
+
+class PrepArgs(C.Structure):
+    _fields_ = [("jobs", PrepJob * 16), ("njobs", C.c_int), ("dtype", C.c_int)]
 
 
 class AdamArgs(C.Structure):
@@ -171,6 +181,8 @@ SYMBOLS = {
     "vmb_channel_gate_bwd": (C.c_int, [C.POINTER(GateBwdArgs), vp]),
     "vmb_fused_adam": (C.c_int, [C.POINTER(AdamArgs), vp]),
     "vmb_pixlin_wgrad": (C.c_int, [C.POINTER(WgradArgs), vp]),
+    "vmb_prep_block_weights": (C.c_int, [C.POINTER(PrepArgs), vp]),
+    "vmb_sum4_add": (C.c_int, [vp, vp, vp, C.c_int, C.c_long, C.c_int, vp]),
 }
 
 

@@ -618,6 +618,89 @@ int fused_adam_launch(const AdamParams& p, cudaStream_t stream) {
     return VMB_OK;
 }
 
+// ------------------------------------------------------------------------------------------ per-step weight preparation
+// One launch per OSS block and step instead of ~35 small torch kernels: every 1x1-conv weight of the block in kernel layout
+// (compute dtype, rows zero-padded to 16 elements) together with its transpose (the data-gradient GEMMs), the folded
+// x_proj / dt_proj matrix  big[k] = [W_dt,k W_x,k[:R] ; W_x,k[R:]]  (MambaSISR6_arch.py:409-414 as ONE contraction on the
+// un-permuted x), A = -exp(A_logs) and the spatially flipped depthwise taps (transposed conv of the backward pass).
+// job types: 0 convert (M x K -> M x ld), 1 convert + transpose (M x K -> K x ld), 2 fold (writes big and its transpose),
+//            3 A = -exp(src) fp32, 4 flip the 9 taps fp32
+template <typename out_t>
+__global__ void __launch_bounds__(256) prep_weights_kernel(const PrepParams p) {
+    const PrepJob j = p.jobs[blockIdx.y];
+    const long stride = (long)gridDim.x * 256;
+    const long i0 = (long)blockIdx.x * 256 + threadIdx.x;
+    if (j.type == 0 || j.type == 1) {
+        out_t* dst = reinterpret_cast<out_t*>(j.dst);
+        const int rows = j.type == 0 ? j.M : j.K, cols = j.type == 0 ? j.K : j.M;
+        for (long i = i0; i < (long)rows * j.ld; i += stride) {
+            const int r = (int)(i / j.ld), c = (int)(i % j.ld);
+            float v = 0.f;
+            if (c < cols) v = j.type == 0 ? j.src[(long)r * j.K + c] : j.src[(long)c * j.K + r];
+            dst[i] = from_f32<out_t>(v);
+        }
+    } else if (j.type == 2) {  // src = x_proj (4, R+2N, C), src2 = dt_w (4, C, R): M = C, K = R, N2 = 2N
+        out_t* big = reinterpret_cast<out_t*>(j.dst);
+        out_t* bigT = reinterpret_cast<out_t*>(j.dst2);
+        const int C = j.M, R = j.K, N2 = j.N2, RN = R + N2, rows = 4 * (C + N2);
+        for (long i = i0; i < (long)rows * C; i += stride) {
+            const int row = (int)(i / C), c = (int)(i % C);
+            const int k = row / (C + N2), d = row % (C + N2);
+            float v;
+            if (d < C) {
+                v = 0.f;
+                for (int r = 0; r < R; ++r) v = fmaf(j.src2[((long)k * C + d) * R + r], j.src[((long)k * RN + r) * C + c], v);
+            } else {
+                v = j.src[((long)k * RN + R + (d - C)) * C + c];
+            }
+            big[(long)row * j.ld + c] = from_f32<out_t>(v);
+            bigT[(long)c * j.ld2 + row] = from_f32<out_t>(v);
+        }
+        // zero the padding columns
+        for (long i = i0; i < (long)rows * (j.ld - C); i += stride) big[(i / (j.ld - C)) * j.ld + C + i % (j.ld - C)] = from_f32<out_t>(0.f);
+        for (long i = i0; i < (long)C * (j.ld2 - rows); i += stride) bigT[(i / (j.ld2 - rows)) * j.ld2 + rows + i % (j.ld2 - rows)] = from_f32<out_t>(0.f);
+    } else if (j.type == 3) {
+        float* dst = reinterpret_cast<float*>(j.dst);
+        for (long i = i0; i < (long)j.M * j.K; i += stride) dst[i] = -expf(j.src[i]);
+    } else {
+        float* dst = reinterpret_cast<float*>(j.dst);
+        for (long i = i0; i < (long)j.M * 9; i += stride) dst[i] = j.src[(i / 9) * 9 + (8 - i % 9)];
+    }
+}
+
+int prep_weights_launch(const PrepParams& p, int dtype, cudaStream_t stream) {
+    dim3 grid(64, p.njobs);
+    switch (dtype) {
+        case VMB_F32: prep_weights_kernel<float><<<grid, 256, 0, stream>>>(p); break;
+        case VMB_BF16: prep_weights_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(p); break;
+        case VMB_F16: prep_weights_kernel<__half><<<grid, 256, 0, stream>>>(p); break;
+        default: set_error("prep_weights: unsupported dtype %d", dtype); return VMB_ERR_INVALID;
+    }
+    VMB_CUDA(cudaGetLastError());
+    return VMB_OK;
+}
+
+// out = add + sum_k x4[:, k]   (the four un-permuted direction gradients of u joined with the x_proj data gradient)
+template <typename in_t>
+__global__ void __launch_bounds__(256) sum4_add_kernel(const in_t* __restrict__ x4, const in_t* __restrict__ add, in_t* __restrict__ out,
+                                                       long per_dir, long per_batch, long total) {
+    pdl_trigger();
+    pdl_wait();
+    constexpr int V = Vec<in_t>::N;
+    for (long i = ((long)blockIdx.x * 256 + threadIdx.x) * V; i < total; i += (long)gridDim.x * 256 * V) {
+        const long b = i / per_dir, o = i % per_dir;
+        float acc[V], t[V];
+        load_vec<in_t>(add + i, acc, V, true);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            load_vec<in_t>(x4 + b * per_batch + k * per_dir + o, t, V, true);
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[e] += t[e];
+        }
+        store_vec<in_t>(out + i, acc, V, true);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------- launchers
 #define VMB_DISPATCH(dtype, KERN, grid, block, ...)                                                    \
     switch (dtype) {                                                                                   \
@@ -744,6 +827,37 @@ extern "C" int vmb_fused_adam(const vmb_adam_args* a, void* stream) {
     AdamParams p{a->param, a->grad, a->exp_avg, a->exp_avg_sq, a->ema, a->state, a->n, a->lr, a->beta1, a->beta2, a->eps,
                  a->weight_decay, a->decoupled_weight_decay, a->grad_scale, a->max_grad_norm, a->ema_decay, a->zero_grad};
     return fused_adam_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vmb_prep_block_weights(const vmb_prep_args* a, void* stream) {
+    VMB_CHECK(a && a->njobs > 0 && a->njobs <= VMB_PREP_MAX_JOBS, "prep_block_weights: 1..%d jobs", VMB_PREP_MAX_JOBS);
+    PrepParams p{};
+    p.njobs = a->njobs;
+    for (int i = 0; i < a->njobs; ++i) {
+        const vmb_prep_job& j = a->jobs[i];
+        VMB_CHECK(j.src && j.dst && j.type >= 0 && j.type <= 4 && j.M > 0 && (j.type == 4 || j.K > 0), "prep_block_weights: bad job %d", i);
+        VMB_CHECK(j.type != 2 || (j.src2 && j.dst2), "prep_block_weights: fold job %d needs src2 / dst2", i);
+        p.jobs[i] = PrepJob{j.src, j.src2, j.dst, j.dst2, j.type, j.M, j.K, j.N2, j.ld, j.ld2};
+    }
+    return prep_weights_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vmb_sum4_add(const void* x4, const void* add, void* out, int batch, long per_dir, int dtype, void* stream) {
+    VMB_CHECK(x4 && add && out && batch > 0 && per_dir > 0, "sum4_add: bad arguments");
+    const int v = dtype == VMB_F32 ? 4 : 8;
+    VMB_CHECK(per_dir % v == 0 && ((reinterpret_cast<uintptr_t>(x4) | reinterpret_cast<uintptr_t>(add) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+              "sum4_add: 16 B aligned contiguous tensors");
+    const long total = (long)batch * per_dir;
+    const int blocks = (int)((total / v + 255) / 256 < 148 * 8 ? (total / v + 255) / 256 : 148 * 8);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (dtype) {
+        case VMB_F32: VMB_CUDA(launch_pdl(sum4_add_kernel<float>, dim3(blocks), dim3(256), 0, st, (const float*)x4, (const float*)add, (float*)out, per_dir, 4 * per_dir, total)); break;
+        case VMB_BF16: VMB_CUDA(launch_pdl(sum4_add_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)x4, (const __nv_bfloat16*)add, (__nv_bfloat16*)out, per_dir, 4 * per_dir, total)); break;
+        case VMB_F16: VMB_CUDA(launch_pdl(sum4_add_kernel<__half>, dim3(blocks), dim3(256), 0, st, (const __half*)x4, (const __half*)add, (__half*)out, per_dir, 4 * per_dir, total)); break;
+        default: set_error("sum4_add: unsupported dtype %d", dtype); return VMB_ERR_INVALID;
+    }
+    VMB_CUDA(cudaGetLastError());
+    return VMB_OK;
 }
 
 extern "C" int vmb_channel_gate_bwd(const vmb_gate_bwd_args* a, void* stream) {

@@ -40,11 +40,21 @@ struct AdamParams {
     float grad_scale, max_norm, ema_decay;
     int zero_grad;
 };
+struct PrepJob {
+    const float* src; const float* src2; void* dst; void* dst2;
+    int type, M, K, N2, ld, ld2;
+};
+struct PrepParams {
+    PrepJob jobs[VMB_PREP_MAX_JOBS];
+    int njobs;
+};
+int prep_weights_launch(const PrepParams& p, int dtype, cudaStream_t stream);
 struct WgradParams {
     const void* dy; const void* x; float* out;
     int B, M, K, L;
     int64_t dy_bs, dy_cs, x_bs, x_cs;
     int splits, per_batch;
+    float* dbias;  // optional: dbias[m] += sum_{b,p} dy[b][m][p]
 };
 int wgrad_launch(const WgradParams& p, int dtype, cudaStream_t stream);
 int fused_adam_launch(const AdamParams& p, cudaStream_t stream);

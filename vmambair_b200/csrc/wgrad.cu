@@ -73,6 +73,8 @@ __global__ void __launch_bounds__(128) wgrad_mma_kernel(const WgradParams p) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
     const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const bool do_bias = p.dbias != nullptr && blockIdx.y == 0;
+    float bsum = 0.f;
 
     stage(0, p_lo);
     int buf = 0;
@@ -84,6 +86,15 @@ __global__ void __launch_bounds__(128) wgrad_mma_kernel(const WgradParams p) {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
+        if (do_bias) {  // row sums of dY (the bias gradient): thread t sums half a row of the staged tile
+            float f[8];
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                unpack8<in_t>(*reinterpret_cast<const uint4*>(&sA[buf][tid >> 1][(tid & 1) * 16 + v * 8]), f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) bsum += f[e];
+            }
+        }
 #pragma unroll
         for (int ks = 0; ks < WG_PK; ks += 16) {
             uint32_t a[2][4], bq[2][4];
@@ -103,6 +114,11 @@ __global__ void __launch_bounds__(128) wgrad_mma_kernel(const WgradParams p) {
                 }
         }
         __syncthreads();
+    }
+    if (do_bias) {
+        bsum += __shfl_xor_sync(0xffffffffu, bsum, 1);
+        const int m = m0 + (tid >> 1);
+        if ((tid & 1) == 0 && m < p.M) atomicAdd(p.dbias + m, bsum);
     }
     float* __restrict__ out = p.out + (p.per_batch ? (int64_t)b * p.M * p.K : 0);
 #pragma unroll
@@ -140,7 +156,7 @@ extern "C" int vmb_pixlin_wgrad(const vmb_wgrad_args* a, void* stream) {
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     VMB_CHECK(al16(a->dy) && al16(a->x) && a->dy_bs % 8 == 0 && a->dy_cs % 8 == 0 && a->x_bs % 8 == 0 && a->x_cs % 8 == 0,
               "pixlin_wgrad: rows must be 16 B aligned (L %% 8 == 0)");
-    WgradParams p{a->dy, a->x, a->out, a->batch, a->M, a->K, a->L, a->dy_bs, a->dy_cs, a->x_bs, a->x_cs, 1, a->per_batch};
+    WgradParams p{a->dy, a->x, a->out, a->batch, a->M, a->K, a->L, a->dy_bs, a->dy_cs, a->x_bs, a->x_cs, 1, a->per_batch, a->dbias};
     // pixel splits: enough CTAs for ~2 waves, at least 512 pixels per CTA
     const long tiles = (long)((a->M + WG_TM - 1) / WG_TM) * ((a->K + WG_TN - 1) / WG_TN) * a->batch;
     int splits = (int)((2 * 148 + tiles - 1) / tiles);

@@ -114,20 +114,21 @@ def selective_scan_fwd(u, delta, A, B, C_, D=None, delta_bias=None, delta_softpl
     return out, ckpt
 
 
-def selective_scan_bwd(u, delta, A, B, C_, D, delta_bias, dout, ckpt, delta_softplus=False):
-    """-> (du, ddelta, dA, dB, dC, dD, ddelta_bias); dB/dC returned in B/C dtype (reference cpp:347)."""
+def selective_scan_bwd(u, delta, A, B, C_, D, delta_bias, dout, ckpt, delta_softplus=False, zeroed=None):
+    """-> (du, ddelta, dA, dB, dC, dD, ddelta_bias); dB/dC returned in B/C dtype (reference cpp:347).
+    zeroed: optional (dA, dD, dbias) pre-zeroed fp32 buffers (the training path hands out slices of one zeroed workspace)."""
     b, d, l, n, g = _check_common(u, delta, A, B, C_, D, delta_bias, "selective_scan_bwd")
     if dout.dtype != u.dtype or tuple(dout.shape) != (b, d, l) or (dout.stride(-1) != 1 and dout.size(-1) != 1):
         raise RuntimeError("selective_scan_bwd: dout must match u in dtype/shape with stride(-1)==1")
     L = _lib.lib()
     du = torch.empty((b, d, l), dtype=u.dtype, device=u.device)
     ddelta = torch.empty((b, d, l), dtype=u.dtype, device=u.device)
-    dA = torch.zeros_like(A)
+    dA = torch.zeros_like(A) if zeroed is None else zeroed[0]
     dB = torch.empty((b, g, n, l), dtype=u.dtype, device=u.device)
     dC = torch.empty((b, g, n, l), dtype=u.dtype, device=u.device)
     ws = torch.empty(L.vmb_scan_bwd_workspace_bytes(b, g, n, l), dtype=torch.uint8, device=u.device)
-    dD = torch.zeros_like(D) if D is not None else None
-    dbias = torch.zeros_like(delta_bias) if delta_bias is not None else None
+    dD = (torch.zeros_like(D) if zeroed is None else zeroed[1]) if D is not None else None
+    dbias = (torch.zeros_like(delta_bias) if zeroed is None else zeroed[2]) if delta_bias is not None else None
     a = _lib.ScanBwdArgs(
         _ptr(u), _ptr(delta), _ptr(A), _ptr(B), _ptr(C_), _ptr(D), _ptr(delta_bias), _ptr(dout), _ptr(ckpt),
         _ptr(du), _ptr(ddelta), _ptr(dA), _ptr(dB), _ptr(dC), _ptr(dD), _ptr(dbias), _ptr(ws),
@@ -291,14 +292,17 @@ def layernorm_fwd(x, mode, w, b):
     return y
 
 
-def layernorm_bwd(x, g, mode, w, add=None, need_param_grads=True):
+def layernorm_bwd(x, g, mode, w, add=None, need_param_grads=True, zeroed=None):
     """-> (dx (B,C,L), dw (C) fp32, db (C) fp32 | None): LayerNorm backward of g [+ add] (the residual branch's gradient)."""
     B, C_, L = x.shape
     assert x.stride(2) == 1 and g.stride(2) == 1 and g.dtype == x.dtype and (add is None or (add.stride(2) == 1 and add.dtype == x.dtype))
     dx = torch.empty((B, C_, L), dtype=x.dtype, device=x.device)
     stats = torch.empty((B, L, 2), dtype=torch.float32, device=x.device)
-    dw = torch.zeros(C_, dtype=torch.float32, device=x.device) if need_param_grads else None
-    db = torch.zeros(C_, dtype=torch.float32, device=x.device) if (need_param_grads and mode == 1) else None
+    if zeroed is not None:
+        dw, db = zeroed[0], (zeroed[1] if mode == 1 else None)
+    else:
+        dw = torch.zeros(C_, dtype=torch.float32, device=x.device) if need_param_grads else None
+        db = torch.zeros(C_, dtype=torch.float32, device=x.device) if (need_param_grads and mode == 1) else None
     a = _lib.LnBwdArgs(_ptr(x), _ptr(g), _ptr(add), _ptr(w), _ptr(dx), _ptr(dw), _ptr(db), _ptr(stats), B, C_, L, mode,
                        x.stride(0), x.stride(1), g.stride(0), g.stride(1), add.stride(0) if add is not None else 0,
                        add.stride(1) if add is not None else 0, dx.stride(0), dx.stride(1), _DT[x.dtype])
@@ -306,7 +310,7 @@ def layernorm_bwd(x, g, mode, w, add=None, need_param_grads=True):
     return dx, dw, db
 
 
-def merge_norm_gate_bwd(ws, z, dy2, dpooled, ln_w, ln_b, C_, L, dz_out):
+def merge_norm_gate_bwd(ws, z, dy2, dpooled, ln_w, ln_b, C_, L, dz_out, zeroed=None):
     """backward of merge_norm_gate(z_preact=True).  ws: the forward's workspace; dy2 (B,C,L) contiguous; dpooled (B,C) fp32|None;
     dz_out: (B,C,L) view receiving the gradient w.r.t. the pre-activation z.  -> (dm (B,C,L), d ln_w, d ln_b)."""
     B = dy2.shape[0]
@@ -314,23 +318,23 @@ def merge_norm_gate_bwd(ws, z, dy2, dpooled, ln_w, ln_b, C_, L, dz_out):
     merged = ws.view(torch.float32)
     stats = merged[B * C_ * L:]
     dm = torch.empty((B, C_, L), dtype=dy2.dtype, device=dy2.device)
-    dw = torch.zeros(C_, dtype=torch.float32, device=dy2.device)
-    db = torch.zeros(C_, dtype=torch.float32, device=dy2.device)
+    dw = torch.zeros(C_, dtype=torch.float32, device=dy2.device) if zeroed is None else zeroed[0]
+    db = torch.zeros(C_, dtype=torch.float32, device=dy2.device) if zeroed is None else zeroed[1]
     a = _lib.MergeBwdArgs(_ptr(merged), _ptr(stats), _ptr(z), _ptr(dy2), _ptr(dpooled), _ptr(ln_w), _ptr(ln_b), _ptr(dm), _ptr(dz_out),
                           _ptr(dw), _ptr(db), B, C_, L, z.stride(0), z.stride(1), dz_out.stride(0), dz_out.stride(1), _DT[dy2.dtype])
     _run("vmb_merge_norm_gate_bwd", a, dy2, "merge_bwd", 0, 2)
     return dm, dw, db
 
 
-def dwconv3x3_bwd(x, w9, bias, g, c_out, H, W, mode):
+def dwconv3x3_bwd(x, w9, bias, g, c_out, H, W, mode, zeroed=None):
     """backward of dwconv3x3 (mode 0 / 1) up to the conv output: -> (dv (B, channels, L), dw9 (channels, 9) fp32, dbias (channels) fp32|None);
     the input gradient is dwconv3x3(dv, w9.flip(-1), None, channels, H, W, 2)."""
     B = x.shape[0]
     ch = c_out * (2 if mode else 1)
     assert g.stride(2) == 1 and x.stride(2) == 1 and g.dtype == x.dtype
     dv = torch.empty((B, ch, H * W), dtype=x.dtype, device=x.device)
-    dw = torch.zeros((ch, 9), dtype=torch.float32, device=x.device)
-    dbias = torch.zeros(ch, dtype=torch.float32, device=x.device) if bias is not None else None
+    dw = torch.zeros((ch, 9), dtype=torch.float32, device=x.device) if zeroed is None else zeroed[0]
+    dbias = (torch.zeros(ch, dtype=torch.float32, device=x.device) if zeroed is None else zeroed[1]) if bias is not None else None
     a = _lib.DwconvBwdArgs(_ptr(x), _ptr(w9), _ptr(bias), _ptr(g), _ptr(dv), _ptr(dw), _ptr(dbias), B, c_out, H, W, mode,
                            x.stride(0), x.stride(1), g.stride(0), g.stride(1), dv.stride(0), dv.stride(1), _DT[x.dtype])
     _run("vmb_dwconv3x3_bwd", a, x, "dwconv_bwd", 0, 2)
@@ -348,9 +352,10 @@ def channel_gate_bwd(dyg, y2, gate, mode):
     return dy2, dg
 
 
-def pixlin_wgrad(dy, x, per_batch=False):
+def pixlin_wgrad(dy, x, per_batch=False, out=None, dbias=None):
     """dW[m,k] = sum_{b,p} dy[b,m,p] x[b,k,p] -> fp32 (M,K)  (or (B,M,K) without the batch sum).  16-bit activations with 16 B aligned
-    rows run this library's mma.sync split-pixel kernel; fp32 (parity mode) or unaligned rows go to the library GEMM."""
+    rows run this library's mma.sync split-pixel kernel; fp32 (parity mode) or unaligned rows go to the library GEMM.
+    out: optional pre-zeroed fp32 result buffer; dbias: optional pre-zeroed (M) fp32 buffer receiving sum_{b,p} dy (the bias gradient)."""
     B, M, L = dy.shape
     K = x.shape[1]
     ok = (dy.dtype in (torch.bfloat16, torch.float16) and x.dtype == dy.dtype and dy.stride(2) == 1 and x.stride(2) == 1
@@ -358,9 +363,39 @@ def pixlin_wgrad(dy, x, per_batch=False):
           and dy.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0)
     if not ok:
         wb = torch.bmm(dy, x.transpose(1, 2)).float()
-        return wb if per_batch else wb.sum(0)
-    out = torch.zeros((B, M, K) if per_batch else (M, K), dtype=torch.float32, device=dy.device)
+        if dbias is not None:
+            dbias += dy.float().sum((0, 2))
+        res = wb if per_batch else wb.sum(0)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+    if out is None:
+        out = torch.zeros((B, M, K) if per_batch else (M, K), dtype=torch.float32, device=dy.device)
     a = _lib.WgradArgs(_ptr(dy), _ptr(x), _ptr(out), B, M, K, L, dy.stride(0), dy.stride(1), x.stride(0), x.stride(1),
-                       int(per_batch), _DT[dy.dtype])
+                       int(per_batch), _DT[dy.dtype], _ptr(dbias))
     _run("vmb_pixlin_wgrad", a, dy, "wgrad")
+    return out
+
+
+def prep_block_weights(jobs, dtype):
+    """jobs: list of (type, src, src2, dst, dst2, M, K, N2, ld, ld2) -- see vmb_prep_block_weights; one launch."""
+    a = _lib.PrepArgs()
+    a.njobs, a.dtype = len(jobs), _DT[dtype]
+    for i, (t, src, src2, dst, dst2, M, K, N2, ld, ld2) in enumerate(jobs):
+        a.jobs[i] = _lib.PrepJob(src.data_ptr(), src2.data_ptr() if src2 is not None else None, dst.data_ptr(),
+                                 dst2.data_ptr() if dst2 is not None else None, t, M, K, N2, ld, ld2)
+    _run("vmb_prep_block_weights", a, jobs[0][1], "prep")
+
+
+def sum4_add(x4, add):
+    """x4 (B,4,C,L) contiguous, add (B,C,L) contiguous -> add + x4.sum(1) (fp32 accumulation, result in the input dtype)"""
+    B = x4.shape[0]
+    assert x4.is_contiguous() and add.is_contiguous() and x4.dtype == add.dtype
+    out = torch.empty_like(add)
+    global _LAUNCHES
+    with torch.cuda.device(x4.device):
+        _lib.check(_lib.lib().vmb_sum4_add(x4.data_ptr(), add.data_ptr(), out.data_ptr(), B, add[0].numel(), _DT[x4.dtype],
+                                           torch.cuda.current_stream(x4.device).cuda_stream), "sum4_add")
+    _LAUNCHES += 1
     return out
