@@ -114,32 +114,9 @@ def workload_name(net):
 
 
 def host_threads():
-    """CPU threads for the CPU arm: PHYSICAL cores inside this process's scheduler affinity mask (respects cpusets / taskset),
-    capped by the cgroup CPU quota.  (All 128 SMT threads of the GPU box ran the oracle 100x slower than its 64 cores.)"""
-    try:
-        aff = os.sched_getaffinity(0)
-    except AttributeError:
-        return os.cpu_count() or 1
-    cores, cur = set(), {}
-    try:
-        for line in open("/proc/cpuinfo"):
-            if ":" in line:
-                k, v = line.split(":", 1)
-                cur[k.strip()] = v.strip()
-            elif cur:
-                if int(cur.get("processor", -1)) in aff:
-                    cores.add((cur.get("physical id"), cur.get("core id")))
-                cur = {}
-    except OSError:
-        pass
-    n = len(cores) if cores else len(aff)
-    try:
-        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
-        if q != "max":
-            n = min(n, max(1, int(q) // int(per)))
-    except (OSError, ValueError):
-        pass
-    return max(1, min(n, len(aff)))
+    """CPU threads for the CPU arm: physical cores inside the affinity mask, capped by the cgroup quota (oracle/cscan.py)"""
+    from oracle import cscan
+    return cscan.host_threads()
 
 
 def bench_input(rank=0):

@@ -30,11 +30,50 @@ def lib():
     if _lib is None:
         build()
         _lib = ctypes.CDLL(_SO)
+        _lib.scan_ref_set_threads(int(host_threads()))  # default: physical cores within the quota, not every SMT thread
     return _lib
 
 
 def set_threads(n: int):
     lib().scan_ref_set_threads(int(n))
+
+
+def host_threads() -> int:
+    """CPU threads for the oracle: PHYSICAL cores inside this process's scheduler affinity mask (cpusets / taskset), capped by the
+    cgroup CPU quota -- on a GPU box with 128 SMT threads and a 16-CPU quota, 128 OpenMP threads run the oracle ~100x slower."""
+    import os
+    try:
+        aff = os.sched_getaffinity(0)
+    except AttributeError:
+        return os.cpu_count() or 1
+    cores, cur = set(), {}
+    try:
+        for line in open("/proc/cpuinfo"):
+            if ":" in line:
+                k, v = line.split(":", 1)
+                cur[k.strip()] = v.strip()
+            elif cur:
+                if int(cur.get("processor", -1)) in aff:
+                    cores.add((cur.get("physical id"), cur.get("core id")))
+                cur = {}
+    except OSError:
+        pass
+    n = len(cores) if cores else len(aff)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(q) // int(per)))
+    except (OSError, ValueError):
+        pass
+    return max(1, min(n, len(aff)))
+
+
+def use_host_threads() -> int:
+    """size the OpenMP scan and torch's intra-op pool for the CPU oracle; returns the thread count"""
+    n = host_threads()
+    set_threads(n)
+    torch.set_num_threads(n)
+    return n
 
 
 def _f32(t):

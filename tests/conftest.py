@@ -12,6 +12,11 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+    # the CPU oracle (torch convs + OpenMP C scan) on the physical cores inside the cgroup quota: all SMT threads of a GPU box
+    # with a small CPU quota make it ~100x slower (the round-2 parity tests took 18 min that way)
+    import torch
+    from oracle import cscan
+    torch.set_num_threads(cscan.host_threads())
 
 
 def pytest_collection_modifyitems(config, items):

@@ -30,7 +30,7 @@ REF_SO = os.path.join(ROOT, "oracle", "_ref", "selective_scan_cuda_core.so")
 
 
 def _oracle(net, x, kind):
-    cscan.set_threads(len(os.sched_getaffinity(0)))
+    cscan.use_host_threads()
     sd = {k: v.detach().float().cpu().clone() for k, v in net.state_dict().items()}
     with torch.no_grad():
         return oss_ref.net_forward(sd, x.float().cpu(), kind)
