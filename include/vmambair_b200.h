@@ -241,6 +241,23 @@ typedef struct {
 } vmb_gate_bwd_args;
 int vmb_channel_gate_bwd(const vmb_gate_bwd_args* a, void* stream);
 
+/* backward of vmb_channel_branch (one CTA per image recomputes the forward in shared memory and walks it backwards).
+ * fwd: the forward's arguments (c_out unused).  dc_out (B,C) fp32: gradient w.r.t. the forward's output.
+ * -> d_pooled (B,C) fp32, fully written (gradient w.r.t. the pooled SUMS); every parameter gradient fp32, ACCUMULATED (zero-filled
+ * by the caller), shaped like its parameter; d_cin_* / d_cout_* NULL exactly when the forward's are.
+ * scratch: vmb_channel_branch_bwd_scratch_bytes(batch, dc, C) bytes.  Shared memory: vmb_channel_branch_bwd_smem_bytes(C, dc, Rc, N)
+ * must be <= 227 KB (C <= 192 for dc = 4; wider levels keep the composed torch path). */
+typedef struct {
+    vmb_channel_args fwd;
+    const float* dc_out; float* d_pooled;
+    float* d_cin_w; float* d_cin_b; float* d_xc_proj; float* d_dtc_w; float* d_dtc_b; float* d_Ac_logs; float* d_Dsc;
+    float* d_cout_w; float* d_cout_b; float* d_cn_w; float* d_cn_b;
+    float* scratch;
+} vmb_channel_bwd_args;
+int vmb_channel_branch_bwd(const vmb_channel_bwd_args* a, void* stream);
+int64_t vmb_channel_branch_bwd_smem_bytes(int C, int dc, int Rc, int N);
+int64_t vmb_channel_branch_bwd_scratch_bytes(int batch, int dc, int C);
+
 /* weight gradient of a 1x1 conv: out[m][k] += sum_{b,p} dy[b][m][p] * x[b][k][p]  (out fp32 (M,K), accumulated: the caller zero-fills;
  * per_batch != 0: out is (B,M,K) and batches are not summed -- the channel gate in front of out_conv scales them per image).
  * dy (B,M,L), x (B,K,L): bf16 / fp16 views with 16 B aligned, pixel-contiguous rows.  mma.sync tensor-core kernel, split over

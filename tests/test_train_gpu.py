@@ -105,3 +105,34 @@ def test_pixlin_wgrad_matches_fp32_contraction(B, M, K, L, per_batch):
     ref = ref if per_batch else ref.sum(0)
     assert got.dtype == torch.float32 and got.shape == ref.shape
     torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-2 * float(ref.abs().max()) * 1e-2 + 1e-3)
+
+
+@pytest.mark.parametrize("variant,dim", [("sisr", 48), ("mamber32", 96), ("mamber33", 32), ("realsr", 64)])
+def test_channel_branch_backward_matches_torch_autograd(variant, dim):
+    """vmb_channel_branch_bwd (one CTA per image) vs torch autograd over SS2D_1.cforward_pooled: dpooled and every channel parameter"""
+    from vmambair_b200 import fused_train
+    torch.manual_seed(11)
+    a = archs.SS2D_1(d_model=dim, ssm_ratio=1, variant=variant).cuda()
+    L = 24 * 16
+    pooled = (torch.randn(3, dim, device="cuda") * L * 0.3)
+    dc = torch.randn(3, dim, device="cuda")
+    names = [n for n, _ in a.named_parameters()]
+    res = {}
+    for path in ("kernel", "torch"):
+        a.zero_grad(set_to_none=True)
+        pp = pooled.clone().requires_grad_()
+        c = fused_train.channel_gate(a, pp, L) if path == "kernel" else a.cforward_pooled(pp * (1.0 / L))
+        if path == "kernel":
+            assert "Channel" in type(c.grad_fn).__name__
+        c.backward(dc)
+        res[path] = (c.detach().clone(), pp.grad.clone(), {n: (p.grad.clone() if p.grad is not None else None) for n, p in a.named_parameters()})
+    ck, dpk, gk = res["kernel"]
+    ct, dpt, gt = res["torch"]
+    torch.testing.assert_close(ck, ct, rtol=1e-3, atol=1e-4)
+    assert (dpk - dpt).abs().max() <= 2e-3 * dpt.abs().max() + 1e-7
+    for n in names:
+        if gt[n] is None:
+            continue
+        assert gk[n] is not None, n
+        tol = 2e-2 if n.endswith("conv_cout.bias") else 3e-3 * float(gt[n].abs().max().clamp_min(1e-6)) + 1e-6
+        assert float((gk[n] - gt[n]).abs().max()) <= tol, (n, float((gk[n] - gt[n]).abs().max()), float(gt[n].abs().max()))

@@ -141,6 +141,12 @@ class WgradArgs(C.Structure):
                 ("dbias", vp)]
 
 
+class ChannelBwdArgs(C.Structure):
+    _fields_ = [("fwd", ChannelArgs), ("dc_out", vp), ("d_pooled", vp),
+                ("d_cin_w", vp), ("d_cin_b", vp), ("d_xc_proj", vp), ("d_dtc_w", vp), ("d_dtc_b", vp), ("d_Ac_logs", vp), ("d_Dsc", vp),
+                ("d_cout_w", vp), ("d_cout_b", vp), ("d_cn_w", vp), ("d_cn_b", vp), ("scratch", vp)]
+
+
 class PrepJob(C.Structure):
     _fields_ = [("src", vp), ("src2", vp), ("dst", vp), ("dst2", vp), ("type", C.c_int), ("M", C.c_int), ("K", C.c_int),
                 ("N2", C.c_int), ("ld", C.c_int), ("ld2", C.c_int)]
@@ -181,6 +187,9 @@ SYMBOLS = {
     "vmb_channel_gate_bwd": (C.c_int, [C.POINTER(GateBwdArgs), vp]),
     "vmb_fused_adam": (C.c_int, [C.POINTER(AdamArgs), vp]),
     "vmb_pixlin_wgrad": (C.c_int, [C.POINTER(WgradArgs), vp]),
+    "vmb_channel_branch_bwd": (C.c_int, [C.POINTER(ChannelBwdArgs), vp]),
+    "vmb_channel_branch_bwd_smem_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vmb_channel_branch_bwd_scratch_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "vmb_prep_block_weights": (C.c_int, [C.POINTER(PrepArgs), vp]),
     "vmb_sum4_add": (C.c_int, [vp, vp, vp, C.c_int, C.c_long, C.c_int, vp]),
 }

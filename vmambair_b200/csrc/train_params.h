@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "../../include/vmambair_b200.h"
+#include "oss_params.h"
 
 namespace vmb {
 struct LnFwdParams {
@@ -57,6 +58,13 @@ struct WgradParams {
     float* dbias;  // optional: dbias[m] += sum_{b,p} dy[b][m][p]
 };
 int wgrad_launch(const WgradParams& p, int dtype, cudaStream_t stream);
+struct ChannelBwdParams {
+    ChannelParams fwd;
+    const float* dc_out; float* d_pooled;
+    float *d_cin_w, *d_cin_b, *d_xc_proj, *d_dtc_w, *d_dtc_b, *d_Ac_logs, *d_Dsc, *d_cout_w, *d_cout_b, *d_cn_w, *d_cn_b;
+    float* scratch_dB;
+};
+int channel_bwd_launch(const ChannelBwdParams& q, cudaStream_t stream);
 int fused_adam_launch(const AdamParams& p, cudaStream_t stream);
 int ln_fwd_launch(const LnFwdParams& p, int dtype, cudaStream_t stream);
 int ln_bwd_launch(const LnBwdParams& p, int dtype, cudaStream_t stream);

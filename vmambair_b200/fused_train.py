@@ -6,12 +6,13 @@ Reference semantics: MamberBlock.forward under autograd, SRGAN/VmambaIR/archs/Ma
 forward_corev1 :395-436, FeedForward :201-218); the training step that drives it is MambaSISRModel.optimize_parameters
 (SRGAN/VmambaIR/models/MambaSISR_model.py:120-147).
 
-Structure (two autograd Functions with the tiny channel-direction branch between them left to torch autograd on (B, C) tensors):
+Structure (three autograd Functions):
     prepare_block: ONE launch per block and step -> every 1x1-conv weight in kernel layout + its transpose, the folded x_proj/dt_proj
              matrix, A = -exp(A_logs), the flipped depthwise taps (vmb_prep_block_weights)
     _Front:  x -> norm1 + in_conv -> dwconv + SiLU -> x_proj/dt_proj (folded GEMM) -> cross-scan -> selective scan (checkpoints)
              -> merge + out_norm + SiLU(z) gate -> (y2, pooled sums)
-    c = SS2D_1.cforward_pooled(pooled / L)                      (torch ops, fp32, a few hundred bytes per image)
+    _Channel: pooled sums -> channel-direction OSS -> c         (vmb_channel_branch / vmb_channel_branch_bwd, one CTA per image;
+             levels whose (2 dc, 16, C) state history exceeds one CTA's shared memory (C = 384) keep torch autograd)
     _Tail:   (y2, c, x) -> channel gate + out_conv + residual -> norm2 + project_in -> dwconv + GELU gate -> project_out + residual
 
 Backward kernels: vmb_pixlin with the transposed weight (data gradients of the five 1x1 convs), vmb_pixlin_wgrad (their weight and bias
@@ -221,6 +222,44 @@ class _Tail(torch.autograd.Function):
                 Z["bpout"] if b_pout is not None else None, None, None, None, None, None, None, None, None)
 
 
+class _Channel(torch.autograd.Function):
+    """channel-direction OSS on the pooled sums: vmb_channel_branch forward, vmb_channel_branch_bwd backward (one CTA per image each)"""
+
+    @staticmethod
+    def forward(ctx, pooled, inv_count, C, dc, Rc, N, cin_w, cin_b, xc_proj, dtc_w, dtc_b, Ac_logs, Dsc, cout_w, cout_b, cn_w, cn_b):
+        prm = dict(cin_w=_f32(cin_w.view(-1)) if cin_w is not None else None, cin_b=_f32(cin_b), xc_proj=_f32(xc_proj), dtc_w=_f32(dtc_w),
+                   dtc_b=_f32(dtc_b), Ac_logs=_f32(Ac_logs), Dsc=_f32(Dsc), cout_w=_f32(cout_w.view(-1)) if cout_w is not None else None,
+                   cout_b=_f32(cout_b), cn_w=_f32(cn_w), cn_b=_f32(cn_b), dc=dc, Rc=Rc, N=N)
+        pooled = pooled.detach().float().contiguous()
+        ctx.prm, ctx.inv_count, ctx.C = prm, inv_count, C
+        ctx.save_for_backward(pooled)
+        ctx.shapes = [None if t is None else t.shape for t in (cin_w, cin_b, xc_proj, dtc_w, dtc_b, Ac_logs, Dsc, cout_w, cout_b, cn_w, cn_b)]
+        return ops.channel_branch(pooled, inv_count, prm, C)
+
+    @staticmethod
+    def backward(ctx, dc_out):
+        (pooled,) = ctx.saved_tensors
+        dpooled, g = ops.channel_branch_bwd(pooled, ctx.inv_count, ctx.prm, ctx.C, dc_out)
+        keys = ("cin_w", "cin_b", "xc_proj", "dtc_w", "dtc_b", "Ac_logs", "Dsc", "cout_w", "cout_b", "cn_w", "cn_b")
+        grads = [None if shp is None else g[k].view(shp) for k, shp in zip(keys, ctx.shapes)]
+        return (dpooled, None, None, None, None, None, *grads)
+
+
+def channel_gate(a, pooled, L):
+    """c (B, C) fp32 from the pooled sums: the fused kernels when the level fits one CTA's shared memory, else torch autograd"""
+    C = pooled.shape[1]
+    prm_probe = dict(dc=a.dc_inner, Rc=a.dtc_rank, N=a.dc_state)
+    if ops.channel_branch_bwd_supported(C, prm_probe):
+        has_cio = hasattr(a, "conv_cin")
+        cn = a.channel_norm.body
+        return _Channel.apply(pooled, 1.0 / L, C, a.dc_inner, a.dtc_rank, a.dc_state,
+                              a.conv_cin.weight if has_cio else None, a.conv_cin.bias if has_cio else None, a.xc_proj_weight,
+                              a.dtc_projs_weight, a.dtc_projs_bias, a.Ac_logs, a.Dsc,
+                              a.conv_cout.weight if has_cio else None, a.conv_cout.bias if has_cio else None, cn.weight, cn.bias)
+    with torch.autocast("cuda", enabled=False):
+        return a.cforward_pooled(pooled * (1.0 / L))
+
+
 def block_forward(block, x: torch.Tensor) -> torch.Tensor:
     """MamberBlock.forward with autograd on the fused kernels (x: (B,C,H,W) CUDA tensor in the compute dtype)."""
     a, f = block.attn, block.ffn
@@ -231,8 +270,7 @@ def block_forward(block, x: torch.Tensor) -> torch.Tensor:
     y2, pooled = _Front.apply(x, n1.weight, getattr(n1, "bias", None), a.in_conv.weight, a.in_conv.bias, a.conv2d.weight,
                               a.conv2d.bias, a.x_proj_weight, a.dt_projs_weight, a.dt_projs_bias, a.A_logs, a.Ds, on.weight, on.bias,
                               P["Win"], P["WinT"], P["Wbig"], P["WbigT"], P["A"], P["cwf"])
-    with torch.autocast("cuda", enabled=False):
-        c = a.cforward_pooled(pooled * (1.0 / L))  # (B, C) fp32, torch autograd (channel-direction OSS on the pooled descriptor)
+    c = channel_gate(a, pooled, L)  # (B, C) fp32: channel-direction OSS on the pooled descriptor
     return _Tail.apply(y2, c, x, a.out_conv.weight, a.out_conv.bias, n2.weight, getattr(n2, "bias", None), f.project_in.weight,
                        f.project_in.bias, f.dwconv.weight, f.dwconv.bias, f.project_out.weight, f.project_out.bias,
                        1 if a.gate == "mul" else 2, P["Wout"], P["WoutT"], P["Wpin"], P["WpinT"], P["Wpout"], P["WpoutT"], P["fdwf"])

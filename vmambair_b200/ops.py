@@ -399,3 +399,41 @@ def sum4_add(x4, add):
                                            torch.cuda.current_stream(x4.device).cuda_stream), "sum4_add")
     _LAUNCHES += 1
     return out
+
+
+def _channel_args(pooled, inv_count, prm, C_, c_out):
+    B = pooled.shape[0]
+    return _lib.ChannelArgs(_ptr(pooled), inv_count, _ptr(prm["cin_w"]), _ptr(prm["cin_b"]), _ptr(prm["xc_proj"]),
+                            _ptr(prm["dtc_w"]), _ptr(prm["dtc_b"]), _ptr(prm["Ac_logs"]), _ptr(prm["Dsc"]), _ptr(prm["cout_w"]),
+                            _ptr(prm["cout_b"]), _ptr(prm["cn_w"]), _ptr(prm["cn_b"]), _ptr(c_out), B, C_, prm["dc"], prm["Rc"], prm["N"])
+
+
+def channel_branch_bwd_supported(C_, prm) -> bool:
+    return prm["N"] <= 16 and 2 * prm["dc"] * 16 <= 512 and \
+        _lib.lib().vmb_channel_branch_bwd_smem_bytes(C_, prm["dc"], prm["Rc"], prm["N"]) <= 227 * 1024
+
+
+def channel_branch_bwd(pooled, inv_count, prm, C_, dc_out):
+    """backward of channel_branch: -> (dpooled (B,C) fp32, dict of fp32 parameter gradients keyed like prm)"""
+    B = pooled.shape[0]
+    dev = pooled.device
+    dc, Rc, N = prm["dc"], prm["Rc"], prm["N"]
+    RN = Rc + 2 * N
+    sizes = dict(cin_w=dc, cin_b=dc, xc_proj=2 * RN * dc, dtc_w=2 * dc * Rc, dtc_b=2 * dc, Ac_logs=2 * dc * N, Dsc=2 * dc, cout_w=dc,
+                 cout_b=1, cn_w=C_, cn_b=C_)
+    flat = torch.zeros(sum(sizes.values()), dtype=torch.float32, device=dev)  # one zero fill for every accumulator
+    g, o = {}, 0
+    for k, n in sizes.items():
+        g[k] = flat[o:o + n]
+        o += n
+    has_cin, has_cout = prm["cin_w"] is not None, prm["cout_w"] is not None
+    dpooled = torch.empty((B, C_), dtype=torch.float32, device=dev)
+    scratch = torch.empty(_lib.lib().vmb_channel_branch_bwd_scratch_bytes(B, dc, C_) // 4, dtype=torch.float32, device=dev)
+    dc_out = dc_out.float().contiguous()
+    a = _lib.ChannelBwdArgs(_channel_args(pooled, inv_count, prm, C_, None), _ptr(dc_out), _ptr(dpooled),
+                            _ptr(g["cin_w"]) if has_cin else None, _ptr(g["cin_b"]) if has_cin else None, _ptr(g["xc_proj"]),
+                            _ptr(g["dtc_w"]), _ptr(g["dtc_b"]), _ptr(g["Ac_logs"]), _ptr(g["Dsc"]),
+                            _ptr(g["cout_w"]) if has_cout else None, _ptr(g["cout_b"]) if has_cout else None, _ptr(g["cn_w"]),
+                            _ptr(g["cn_b"]), _ptr(scratch))
+    _run("vmb_channel_branch_bwd", a, pooled, "channel_bwd")
+    return dpooled, g
