@@ -47,7 +47,7 @@ __device__ __forceinline__ void red_add_f32x4_g(float4* addr, float4 v) {
 }
 
 template <typename in_t, int RB, int SS>
-__global__ void __launch_bounds__(128, 2) scan_bwd_tma_kernel(const ScanBwdParams p, const __grid_constant__ ScanBwdTmaMaps maps) {
+__global__ void __launch_bounds__(128, sizeof(in_t) == 4 ? 1 : 2) scan_bwd_tma_kernel(const ScanBwdParams p, const __grid_constant__ ScanBwdTmaMaps maps) {
     pdl_wait();
     using K = BwdTmaCfg<in_t, RB, SS>;
     using Cfg = FwdCfg<RB>;
@@ -353,7 +353,7 @@ static int launch_bt3(const ScanBwdParams& p, const ScanBwdTmaMaps& maps, cudaSt
     using K = BwdTmaCfg<in_t, RB, SS>;
     auto kern = scan_bwd_tma_kernel<in_t, RB, SS>;
     constexpr size_t smem = K::smem_bytes + 128;
-    static_assert(smem <= 113 * 1024, "scan_bwd_tma: two CTAs per SM");
+    static_assert(sizeof(in_t) == 4 ? smem <= 227 * 1024 : smem <= 113 * 1024, "scan_bwd_tma: two CTAs per SM (one for fp32 I/O)");
     VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long blocks = (long)p.batch * (p.dim / K::ROWS);
     VMB_CUDA(launch_pdl(kern, dim3((unsigned)blocks), dim3(128), smem, stream, p, maps));
@@ -379,7 +379,7 @@ static int launch_bt1(const ScanBwdParams& p, const ScanBwdTmaMaps& maps, int rb
 bool scan_bwd_tma_pick(const ScanBwdParams& p, int dtype, int& rb, int& ss) {
     const char* e = getenv("VMB_SCAN_BWD_TMA");
     if (e && atoi(e) == 0) return false;
-    if (dtype == VMB_F32) return false;  // fp32 tiles need > 113 KB per CTA: the generic kernel keeps fp32 I/O
+    if (dtype == VMB_F32 && getenv("VMB_SCAN_BWD_TMA_F32") && atoi(getenv("VMB_SCAN_BWD_TMA_F32")) == 0) return false;
     if (!p.vec_ok || p.npad != 16 || p.L < 512 || p.ckpt == nullptr) return false;
     const int rpg = p.rows_per_group;
     const long rows = (long)p.batch * p.dim;
@@ -415,6 +415,7 @@ int scan_bwd_tma_launch(const ScanBwdParams& p, int dtype, int rb, int ss, cudaS
     if ((rc = make_tmap_4d(&maps.b, dtype, p.Bm, dbc, sb, box_bc)) != VMB_OK) return rc;
     if ((rc = make_tmap_4d(&maps.c, dtype, p.Cm, dbc, sc, box_bc)) != VMB_OK) return rc;
     switch (dtype) {
+        case VMB_F32: return launch_bt1<float>(p, maps, rb, ss, stream);  // 130 KB of tiles: one CTA per SM
         case VMB_BF16: return launch_bt1<__nv_bfloat16>(p, maps, rb, ss, stream);
         case VMB_F16: return launch_bt1<__half>(p, maps, rb, ss, stream);
     }
