@@ -89,7 +89,7 @@ def test_dwconv_modes(dtype, H, W):
     close(o2, (F.gelu(conv_nb[:, :C]) * conv_nb[:, C:]).flatten(2), dtype, scale=2.0)
 
 
-@pytest.mark.parametrize("H,W", [(64, 64), (16, 24), (5, 3)])
+@pytest.mark.parametrize("H,W", [(64, 64), (16, 24), (5, 3), (72, 40), (128, 136)])
 def test_cross_scan_bit_exact(H, W, golden_dir):
     """the six-direction gather must be bit-exact (BASELINE.json): compare with the reference's index maps."""
     from vmambair_b200 import ops
@@ -109,6 +109,13 @@ def test_cross_scan_bit_exact(H, W, golden_dir):
     assert torch.equal(out, ref)
     xb = x.to(torch.bfloat16)
     assert torch.equal(ops.cross_scan([xb.view(B, C, H * W)] * 4, C, H, W)[:, 1], xb.transpose(2, 3).flatten(2))
+    # 16-bit, distinct sources, all four orders (the 16 B-vector kernel when H, W are multiples of 8)
+    bb = big.to(torch.bfloat16)
+    outb = ops.cross_scan([bb[:, k, :C] for k in range(4)], C, H, W)
+    vb = [bb[:, k, :C].reshape(B, C, H, W) for k in range(4)]
+    refb = torch.stack([vb[0].flatten(2), vb[1].transpose(2, 3).flatten(2), vb[2].flatten(2).flip(-1),
+                        vb[3].transpose(2, 3).flatten(2).flip(-1)], 1)
+    assert torch.equal(outb, refb)
 
 
 def test_cross_scan_matches_reference_golden(golden_dir):

@@ -252,9 +252,109 @@ __global__ void __launch_bounds__(256) cross_scan_kernel(const CrossScanParams p
     }
 }
 
+
+// Vectorised variant (H % 8 == 0, W % 8 == 0, 16 B aligned rows; 16-bit and fp32 I/O): a CTA owns a 64 x 64 pixel tile of one row,
+// loads it with 16 B vectors, and writes the four orders as 16 B vectors -- 8 consecutive w for the row-major orders (reversed
+// in-register for k = 2), 8 consecutive h gathered from the fp32 smem tile for the column-major orders.  8x fewer load / store
+// instructions than the per-element kernel above (which stays as the fallback for odd geometries).
+template <typename in_t>
+__global__ void __launch_bounds__(256) cross_scan_vec_kernel(const CrossScanParams p) {
+    pdl_trigger();
+    pdl_wait();
+    constexpr int V = Vec<in_t>::N;           // 8 (16-bit) or 4 (fp32) elements per 16 B
+    constexpr int TS = 64;
+    extern __shared__ float cs_tile[];        // [nsrc][TS][TS + 1]
+    const int tiles_w = (p.W + TS - 1) / TS;
+    const int h0 = (blockIdx.x / tiles_w) * TS, w0 = (blockIdx.x % tiles_w) * TS;
+    const int row = blockIdx.y, b = blockIdx.z;
+    const int L = p.H * p.W;
+    const bool same = p.src[0] == p.src[1] && p.src[0] == p.src[2] && p.src[0] == p.src[3];
+    const int nsrc = same ? 1 : 4;
+    for (int k = 0; k < nsrc; ++k) {
+        const in_t* __restrict__ s = reinterpret_cast<const in_t*>(p.src[k]) + (int64_t)b * p.src_bs + (int64_t)row * p.src_rs;
+        float* t = cs_tile + k * TS * (TS + 1);
+        for (int it = threadIdx.x; it < TS * (TS / V); it += 256) {
+            const int hh = it / (TS / V), wv = (it % (TS / V)) * V;
+            const int h = h0 + hh, w = w0 + wv;
+            float f[V];
+            if (h < p.H && w < p.W) load_vec<in_t>(s + (int64_t)h * p.W + w, f, V, true);  // W % V == 0: whole vectors
+            else {
+#pragma unroll
+                for (int i = 0; i < V; ++i) f[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < V; ++i) t[hh * (TS + 1) + wv + i] = f[i];
+        }
+    }
+    __syncthreads();
+    in_t* __restrict__ o = reinterpret_cast<in_t*>(p.out) + (int64_t)b * p.out_bs + (int64_t)row * L;
+    const float* t0 = cs_tile;
+    const float* t1 = cs_tile + (same ? 0 : 1) * TS * (TS + 1);
+    const float* t2 = cs_tile + (same ? 0 : 2) * TS * (TS + 1);
+    const float* t3 = cs_tile + (same ? 0 : 3) * TS * (TS + 1);
+    for (int it = threadIdx.x; it < TS * (TS / V); it += 256) {
+        {  // row-major orders: V consecutive w of image row h
+            const int hh = it / (TS / V), wv = (it % (TS / V)) * V;
+            const int h = h0 + hh, w = w0 + wv;
+            if (h < p.H && w < p.W) {
+                const int l = h * p.W + w;
+                float f[V], r[V];
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    f[i] = t0[hh * (TS + 1) + wv + i];
+                    r[V - 1 - i] = t2[hh * (TS + 1) + wv + i];
+                }
+                store_vec<in_t>(o + l, f, V, true);
+                store_vec<in_t>(o + 2 * p.out_ks + (L - l - V), r, V, true);  // positions L-1-l ... L-1-(l+V-1), ascending in memory
+            }
+        }
+        {  // column-major orders: V consecutive h of image column w
+            const int ww = it / (TS / V), hv = (it % (TS / V)) * V;
+            const int w = w0 + ww, h = h0 + hv;
+            if (h < p.H && w < p.W) {
+                const int l = w * p.H + h;
+                float f[V], r[V];
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    f[i] = t1[(hv + i) * (TS + 1) + ww];
+                    r[V - 1 - i] = t3[(hv + i) * (TS + 1) + ww];
+                }
+                store_vec<in_t>(o + p.out_ks + l, f, V, true);
+                store_vec<in_t>(o + 3 * p.out_ks + (L - l - V), r, V, true);
+            }
+        }
+    }
+}
+
 int cross_scan_launch(const CrossScanParams& p, int dtype, cudaStream_t stream) {
     dim3 grid(((p.H + 31) / 32) * ((p.W + 31) / 32), p.rows, p.B);
     VMB_CHECK(p.rows <= 65535 && p.B <= 65535, "cross_scan: too many rows / batch");
+    {
+        const int v = dtype == VMB_F32 ? 4 : 8;
+        auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+        const char* ve = getenv("VMB_CROSS_SCAN_V");
+        const bool want = !ve || atoi(ve) != 1;
+        if (want && p.H % v == 0 && p.W % v == 0 && al16(p.src[0]) && al16(p.src[1]) && al16(p.src[2]) && al16(p.src[3]) && al16(p.out) &&
+            p.src_bs % v == 0 && p.src_rs % v == 0 && p.out_bs % v == 0 && p.out_ks % v == 0) {
+            const bool same = p.src[0] == p.src[1] && p.src[0] == p.src[2] && p.src[0] == p.src[3];
+            const size_t smem = sizeof(float) * (same ? 1 : 4) * 64 * 65;
+            dim3 gv(((p.H + 63) / 64) * ((p.W + 63) / 64), p.rows, p.B);
+#define VMB_CSV(T)                                                                                                        \
+    {                                                                                                                     \
+        if (smem > 48 * 1024) VMB_CUDA(cudaFuncSetAttribute(cross_scan_vec_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        VMB_CUDA(launch_pdl(cross_scan_vec_kernel<T>, gv, dim3(256), smem, stream, p));                                    \
+    }
+            switch (dtype) {
+                case VMB_F32: VMB_CSV(float) break;
+                case VMB_BF16: VMB_CSV(__nv_bfloat16) break;
+                case VMB_F16: VMB_CSV(__half) break;
+                default: set_error("cross_scan: unsupported dtype %d", dtype); return VMB_ERR_INVALID;
+            }
+#undef VMB_CSV
+            VMB_CUDA(cudaGetLastError());
+            return VMB_OK;
+        }
+    }
     switch (dtype) {
         case VMB_F32: VMB_CUDA(launch_pdl(cross_scan_kernel<float>, grid, dim3(256), 0, stream, p)); break;
         case VMB_BF16: VMB_CUDA(launch_pdl(cross_scan_kernel<__nv_bfloat16>, grid, dim3(256), 0, stream, p)); break;
