@@ -10,8 +10,9 @@
 //     batch 4, each converting its own tile) -> RB = 2 rows per warp is affordable: 768 warps at batch 4, 4-8 per SM;
 //   * state split (SS): the 8 state pairs of a row over SS warps at small batch; the per-position sums over states (s1, s2) meet in
 //     shared memory, du / ddelta are written by the first warp of the row slot;
-//   * the dB/dC row reduction keeps the warp-local smem transpose + one red.global.add.v4.f32 per (pair, position, warp), with a
-//     padded cell layout (the round-1 layout had 13.7 M shared-memory bank conflicts per launch).
+//   * the dB/dC row reduction: warp-local smem transpose ([row][segment][T + 1] float4: the (row, segment) lanes write without bank
+//     conflicts, the position-per-lane reads are contiguous; the round-1 layout had 13.7 M conflicts per launch), then the warps of the CTA that share the state pair meet at a named barrier and issue ONE
+//     red.global.add.v4.f32 per (pair, position, CTA).
 #include <stdlib.h>
 
 #include "scan_tma_common.cuh"
@@ -30,7 +31,8 @@ struct BwdTmaCfg {
     static constexpr int ROWS = RB * (NW / SS);
     static constexpr int NPW = 8 / SS;
     static constexpr int CELLS = SEGW * T;                      // positions of a warp-chunk (= CHUNK)
-    static constexpr int RED_F4 = CELLS * RB + CELLS / 8 + 8;   // float4 slots of one warp's dB/dC transpose (1 pad slot per 8 cells)
+    static constexpr int RED_RS = SEGW * (T + 1) + 4;           // float4 slots of one row of a warp's dB/dC transpose: [segment][T + 1 pad] (+4: rows half a wavefront apart)
+    static constexpr int RED_F4 = RED_RS * RB + 8;              // (odd segment pitch: conflict-free writes by (row, segment) lanes, contiguous reads)
     static constexpr size_t io_bytes = sizeof(in_t) * (size_t)ROWS * CHUNK;  // one of rawU / rawD / rawG
     static constexpr size_t bc_bytes = sizeof(in_t) * (size_t)16 * CHUNK;
     static constexpr size_t tile_bytes = sizeof(float4) * (size_t)16 * SLOTS;
@@ -46,6 +48,18 @@ __device__ __forceinline__ void red_add_f32x4_g(float4* addr, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+
+// named barrier BASE + idx (idx < 4) with an immediate id, so that ptxas counts the barriers really used
+template <int BASE>
+__device__ __forceinline__ void named_bar_sync(int idx, int count) {
+    switch (idx) {
+        case 0: asm volatile("bar.sync %0, %1;" ::"n"(BASE), "r"(count) : "memory"); break;
+        case 1: asm volatile("bar.sync %0, %1;" ::"n"(BASE + 1), "r"(count) : "memory"); break;
+        case 2: asm volatile("bar.sync %0, %1;" ::"n"(BASE + 2), "r"(count) : "memory"); break;
+        default: asm volatile("bar.sync %0, %1;" ::"n"(BASE + 3), "r"(count) : "memory"); break;
+    }
+}
+
 template <typename in_t, int RB, int SS>
 __global__ void __launch_bounds__(128, sizeof(in_t) == 4 ? 1 : 2) scan_bwd_tma_kernel(const ScanBwdParams p, const __grid_constant__ ScanBwdTmaMaps maps) {
     pdl_wait();
@@ -53,6 +67,7 @@ __global__ void __launch_bounds__(128, sizeof(in_t) == 4 ? 1 : 2) scan_bwd_tma_k
     using Cfg = FwdCfg<RB>;
     constexpr int SEGW = Cfg::SEGW, CHUNK = Cfg::CHUNK, SEGQ = Cfg::SEGQ, SLOTS = Cfg::SLOTS;
     constexpr int V = Vec<in_t>::N, NW = K::NW, NT = 32 * NW, ROWS = K::ROWS, NPW = K::NPW;
+    constexpr int GW = NW / SS;  // warps of the CTA that share a state-pair set (different rows of the same group)
 
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem_raw = smem_dyn + ((128u - (smem_addr(smem_dyn) & 127u)) & 127u);
@@ -244,6 +259,8 @@ __global__ void __launch_bounds__(128, sizeof(in_t) == 4 ? 1 : 2) scan_bwd_tma_k
             // ---- R2: true dh_t and the gradient terms ----
             const float2 A2r = mul2(A2, make_float2(kLn2, kLn2));  // un-scaled A
             float2 dA2 = make_float2(0.f, 0.f);
+            // the warps that share this pair set have finished reading every sRed of the previous pair (deferred second barrier)
+            if (GW > 1 && np > sp * NPW) named_bar_sync<1 + (SS > 1 ? GW : 0)>(SS > 1 ? sp : 0, 32 * GW);
 #pragma unroll
             for (int t = T - 2; t >= 0; t -= 2) {
                 const float4 Bq = bq[t / 2];
@@ -262,8 +279,7 @@ __global__ void __launch_bounds__(128, sizeof(in_t) == 4 ? 1 : 2) scan_bwd_tma_k
                     const float2 vB = mul2(dh, make_float2(dtu[tt], dtu[tt]));
                     const float2 hh = add2(g2[tt], mul2(make_float2(dtu[tt], dtu[tt]), Bv));
                     const float2 vC = mul2(hh, make_float2(go[tt], go[tt]));
-                    const int cell = sl * T + tt;
-                    sRed[cell * RB + (cell >> 3) + ((r + tt) % RB)] = make_float4(vB.x, vB.y, vC.x, vC.y);
+                    sRed[r * K::RED_RS + sl * (T + 1) + tt] = make_float4(vB.x, vB.y, vC.x, vC.y);
                 }
             }
             // dA: reduce over the warp's segments, accumulate in smem (single writer per (row, n))
@@ -277,20 +293,48 @@ __global__ void __launch_bounds__(128, sizeof(in_t) == 4 ? 1 : 2) scan_bwd_tma_k
                 *da = add2(*da, dA2);
             }
             __syncwarp();
-            // dB/dC: sum the RB rows of each (segment, position) cell, one vector reduction per cell
+            if (GW > 1) {
+                // dB/dC: the GW warps of the CTA that work on this pair set (different rows of the same group) meet, then each sums
+                // the RB * GW rows of its share of the cells: ONE vector reduction per (pair, position, CTA) instead of one per warp
+                // (the global reductions were 19-25 % of the kernel, tools/scan_bwd_nored.py)
+                named_bar_sync<1 + (SS > 1 ? GW : 0)>(SS > 1 ? sp : 0, 32 * GW);
+                constexpr int CPW = K::CELLS / GW;
 #pragma unroll
-            for (int cell = lane; cell < K::CELLS; cell += 32) {
-                const float4* src = sRed + cell * RB + (cell >> 3);
-                float4 acc = src[0];
+                for (int i = lane; i < CPW; i += 32) {
+                    const int cell = rs * CPW + i;
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int j = 1; j < RB; ++j) {
-                    const float4 v = src[j];
-                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                    float2 acc_b = make_float2(0.f, 0.f), acc_c = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int w = 0; w < GW; ++w) {
+                        const float4* src = reinterpret_cast<const float4*>(after_tile + (size_t)(w * SS + sp) * K::warp_bytes) + (cell / T) * (T + 1) + cell % T;
+#pragma unroll
+                        for (int j = 0; j < RB; ++j) {
+                            const float4 v = src[j * K::RED_RS];
+                            acc_b = add2(acc_b, make_float2(v.x, v.y));
+                            acc_c = add2(acc_c, make_float2(v.z, v.w));
+                        }
+                    }
+                    acc = make_float4(acc_b.x, acc_b.y, acc_c.x, acc_c.y);
+                    const int l = c0 + cell;
+                    if (l < L && n0 < N && !p.debug_nored) red_add_f32x4_g(scratch + (int64_t)np * L + l, acc);
                 }
-                const int l = c0 + cell;
-                if (l < L && n0 < N && !p.debug_nored) red_add_f32x4_g(scratch + (int64_t)np * L + l, acc);
+            } else {
+                // dB/dC: sum the RB rows of each (segment, position) cell, one vector reduction per cell
+#pragma unroll
+                for (int cell = lane; cell < K::CELLS; cell += 32) {
+                    const float4* src = sRed + (cell / T) * (T + 1) + cell % T;
+                    float4 acc = src[0];
+#pragma unroll
+                    for (int j = 1; j < RB; ++j) {
+                        const float4 v = src[j * K::RED_RS];
+                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                    }
+                    const int l = c0 + cell;
+                    if (l < L && n0 < N && !p.debug_nored) red_add_f32x4_g(scratch + (int64_t)np * L + l, acc);
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
 
         if (SS > 1) {  // sums over the states handled by the other warps of this row slot
@@ -302,7 +346,7 @@ __global__ void __launch_bounds__(128, sizeof(in_t) == 4 ? 1 : 2) scan_bwd_tma_k
                     pp[(((sp - 1) * 2 + 1) * T + t) * 32 + lane] = s2[t];
                 }
             }
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + rs), "r"(32 * SS) : "memory");
+            named_bar_sync<1>(rs, 32 * SS);
             if (sp > 0) continue;
 #pragma unroll
             for (int s = 0; s < SS - 1; ++s)
