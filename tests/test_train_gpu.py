@@ -65,6 +65,37 @@ def test_block_fused_training_path_matches_composed_autograd(variant, dim):
         assert float((a - b).abs().max()) <= tol, (n, float((a - b).abs().max()), float(b.abs().max()))
 
 
+@pytest.mark.parametrize("variant,dim", [("sisr", 48), ("mamber32", 32)])
+def test_direct_grad_accumulation_equals_autograd_accumulation(variant, dim):
+    """fused_train.set_direct_grads(True) (what optim.FlatAdam switches on): the backward kernels add into existing fp32 .grad buffers
+    and autograd receives None -- the resulting .grad must equal the AccumulateGrad route, including accumulation over two backwards"""
+    from vmambair_b200 import fused_train
+    torch.manual_seed(7)
+    archs.set_train_path("fused")
+    blk = archs.MamberBlock(dim=dim, num_heads=1, ffn_expansion_factor=2.66, bias=False, LayerNorm_type="WithBias", variant=variant).cuda()
+    x = torch.randn(2, dim, 16, 24, device="cuda")
+    dout = torch.randn(2, dim, 16, 24, device="cuda")
+    res = {}
+    try:
+        for direct in (False, True):
+            fused_train.set_direct_grads(direct)
+            for p in blk.parameters():
+                p.grad = torch.zeros_like(p)
+            ptrs = [p.grad.data_ptr() for p in blk.parameters()]
+            for _ in range(2):  # two micro-steps accumulate
+                xx = x.clone().requires_grad_()
+                blk(xx).backward(dout)
+            assert ptrs == [p.grad.data_ptr() for p in blk.parameters()]  # the buffers were written in place
+            res[direct] = [xx.grad.clone()] + [p.grad.clone() for p in blk.parameters()]
+    finally:
+        fused_train.set_direct_grads(False)
+    names = ["x"] + [n for n, _ in blk.named_parameters()]
+    for n, a, b in zip(names, res[True], res[False]):
+        tol = 2e-2 if n.endswith("conv_cout.bias") else 1e-4 * float(b.abs().max().clamp_min(1e-6)) + 1e-6
+        assert float((a - b).abs().max()) <= tol, (n, float((a - b).abs().max()), float(b.abs().max()))
+    assert all(float(g.abs().max()) > 0 for n, g in zip(names, res[True]) if not n.endswith("conv_cout.bias")), "a gradient stayed zero"
+
+
 def test_block_fused_training_bf16_close_to_fp32():
     """bf16 activations / fp32 parameters (the autocast training configuration): gradients within bf16 noise of the fp32 run"""
     torch.manual_seed(5)

@@ -12,6 +12,13 @@ SHAPES = [("in_conv96", 96, 192, "ln_act"), ("w_big96", 96, 256, "plain"), ("out
           ("pin96", 96, 510, "ln"), ("pout96", 255, 96, "res"),
           ("in_conv48", 48, 96, "ln_act"), ("w_big48", 48, 160, "plain"), ("out_conv48", 48, 48, "gate_res"),
           ("pin48", 48, 254, "ln"), ("pout48", 127, 48, "res")]
+if os.environ.get("PB_TRAIN"):  # the GEMMs of one training block (forward + data gradients), C = 96 and C = 48
+    SHAPES = [("in_conv96", 96, 192, "ln"), ("w_big96", 96, 512, "plain"), ("out_conv96", 96, 96, "gate_res"), ("pin96", 96, 510, "ln"),
+              ("pout96", 255, 96, "res"), ("d_pout96", 96, 255, "plain"), ("d_pin96", 510, 96, "plain"), ("d_out96", 96, 96, "plain"),
+              ("d_big96", 512, 96, "plain"), ("d_in96", 192, 96, "plain"),
+              ("in_conv48", 48, 96, "ln"), ("w_big48", 48, 320, "plain"), ("out_conv48", 48, 48, "gate_res"), ("pin48", 48, 254, "ln"),
+              ("pout48", 127, 48, "res"), ("d_pout48", 48, 127, "plain"), ("d_pin48", 254, 48, "plain"), ("d_out48", 48, 48, "plain"),
+              ("d_big48", 320, 48, "plain"), ("d_in48", 96, 48, "plain")]
 for name, K, M, kind in SHAPES:
     sets = []
     for _ in range(4):

@@ -574,7 +574,11 @@ bool pixlin_tc_applicable(const PixlinParams& p, int dtype, int out_dtype) {
     // M > 256 (project_in, C=96) or with K <= 64 and M > 128 (project_in, C=48); everything else stays on mma.sync
     const long tiles = (long)(p.P / TC_PT) * p.B;
     const bool has_pro = p.ln_mode != 0 || p.gate_mode != 0;
-    if (tiles < 4L * tc_num_sms()) return false;
+    if (tiles < 3L * tc_num_sms()) return false;
+    // 3-4 tiles per SM (the training step's B = 4, 64x64; round 2, `PB_TRAIN=1 PB_B=4 tools/pixlin_bench.py`): the mma.sync kernel has
+    // only 1-2 CTAs per SM there and loses on every shape but the gate prologue and the reduction-heavy K > 128 -> M <= 64 ones
+    // (e.g. 96 -> 512: 13.7 vs 22.7 us, LayerNorm 96 -> 510: 18.8 vs 30.7 us, 254 -> 48: 9.9 vs 7.1 us)
+    if (tiles < 4L * tc_num_sms()) return p.gate_mode == 0 && !(p.K > 128 && p.M <= 64);
     if (!has_pro) return p.K > 128 || p.M > 128;
     return p.gate_mode == 0 && (p.M > 2 * TC_MT || (p.K <= 64 && p.M > TC_MT));
 }

@@ -37,6 +37,28 @@ def _p16(n):
     return (n + 15) // 16 * 16
 
 
+def _acc(param, fallback):
+    """fp32 accumulator of a parameter gradient: the parameter's own .grad when it is a contiguous fp32 buffer on the same device (the
+    kernels ADD into it -- what autograd's AccumulateGrad would do with one more launch per parameter; with optim.FlatAdam the .grad
+    buffers are views of the flat gradient the all-reduce and the optimizer kernel read), else the zero-filled `fallback` slice.
+    -> (buffer shaped like fallback, direct?)"""
+    g = getattr(param, "grad", None) if param is not None else None
+    if _DIRECT_GRADS and g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.device == fallback.device and \
+            g.numel() == fallback.numel() and not torch.is_grad_enabled():
+        return g.view(fallback.shape), True
+    return fallback, False
+
+
+_DIRECT_GRADS = False  # opt-in (optim.FlatAdam turns it on): only valid for .backward()-style accumulation into .grad
+
+
+def set_direct_grads(on: bool):
+    """True: the backward kernels add the parameter gradients straight into existing fp32 .grad buffers and hand autograd None for
+    them (valid for loss.backward() accumulation, NOT for torch.autograd.grad(...)); False: gradients are returned to autograd"""
+    global _DIRECT_GRADS
+    _DIRECT_GRADS = bool(on)
+
+
 class _Arena:
     """views carved out of one flat tensor (16-element aligned offsets)"""
 
@@ -114,7 +136,7 @@ class _Front(torch.autograd.Function):
             y2, pooled, ws = ops.merge_norm_gate(ys.view(B, 4, C, L), xz[:, C:], _f32(on_w), _f32(on_b), C, H, W,
                                                  z_preact=True, return_ws=True)
             ctx.save_for_backward(x3, xz, xc, xs, dts, bc, ckpt, ws, A, n1w, n1b, w_in, cw, cb, x_proj_w, dt_w, dt_b, Ds, on_w, on_b,
-                                  WinT, WbigT, cwf)
+                                  WinT, WbigT, cwf, b_in)
             ctx.geom = (B, C, H, W, N, R, ln_mode)
         return y2.view(B, C, H, W), pooled
 
@@ -122,7 +144,7 @@ class _Front(torch.autograd.Function):
     def backward(ctx, dy2, dpooled):
         with torch.autocast("cuda", enabled=False):
             (x3, xz, xc, xs, dts, bc, ckpt, ws, A, n1w, n1b, w_in, cw, cb, x_proj_w, dt_w, dt_b, Ds, on_w, on_b,
-             WinT, WbigT, cwf) = ctx.saved_tensors
+             WinT, WbigT, cwf, b_in) = ctx.saved_tensors
             B, C, H, W, N, R, ln_mode = ctx.geom
             L, dt_, dev = H * W, x3.dtype, x3.device
             Mb = 4 * (C + 2 * N)
@@ -134,12 +156,14 @@ class _Front(torch.autograd.Function):
             dy2 = dy2.to(dt_).contiguous().view(B, C, L)
             dpooled = None if dpooled is None else dpooled.float().contiguous()
             dxz = torch.empty_like(xz)  # [d x_pre | d z_pre]
+            (g_onw, k_onw), (g_onb, k_onb) = _acc(on_w, Z["onw"]), _acc(on_b, Z["onb"])
             dm, d_onw, d_onb = ops.merge_norm_gate_bwd(ws, xz[:, C:], dy2, dpooled, _f32(on_w), _f32(on_b), C, L, dz_out=dxz[:, C:],
-                                                       zeroed=(Z["onw"], Z["onb"]))
+                                                       zeroed=(g_onw, g_onb))
             dys = ops.cross_scan([dm] * 4, C, H, W)  # gradient of the merged output, gathered into the four scan orders
+            (g_dD, k_dD), (g_dbias, k_dbias) = _acc(Ds, Z["dD"]), _acc(dt_b, Z["dbias"])
             du, ddelta, dA, dB, dC, dD, dbias = ops.selective_scan_bwd(
                 xs.view(B, 4 * C, L), dts.view(B, 4 * C, L), A, bc[:, :, :N], bc[:, :, N:], _f32(Ds), _f32(dt_b.reshape(-1)),
-                dys.view(B, 4 * C, L), ckpt, True, zeroed=(Z["dA"], Z["dD"], Z["dbias"]))
+                dys.view(B, 4 * C, L), ckpt, True, zeroed=(Z["dA"], g_dD, g_dbias))
             # back to pixel order: pi_k^-1 is pi_k with H and W swapped
             dxc4 = ops.cross_scan([du.view(B, 4, C, L)[:, k] for k in range(4)], C, W, H)
             ddbl = torch.empty((B, 4, C + 2 * N, L), dtype=dt_, device=dev)
@@ -153,16 +177,21 @@ class _Front(torch.autograd.Function):
             d_xproj = torch.cat([torch.bmm(dtw.transpose(1, 2), dbig[:, :C]), dbig[:, C:]], 1)  # [W_dt^T dW ; dW[C:]]
             d_dtw = torch.bmm(dbig[:, :C], xw[:, :R].transpose(1, 2))                            # dW W_x[:R]^T
             # depthwise conv + SiLU
-            dv, d_cw, d_cb = ops.dwconv3x3_bwd(xz[:, :C], _f32(cw.view(C, 9)), _f32(cb), dxc, C, H, W, 0, zeroed=(Z["dcw"], Z["dcb"]))
+            (g_cw, k_cw), (g_cb, k_cb) = _acc(cw, Z["dcw"]), _acc(cb, Z["dcb"])
+            dv, d_cw, d_cb = ops.dwconv3x3_bwd(xz[:, :C], _f32(cw.view(C, 9)), _f32(cb), dxc, C, H, W, 0, zeroed=(g_cw, g_cb))
             ops.dwconv3x3(dv, cwf, None, C, H, W, 2, out=dxz[:, :C])
             # in_conv + norm1
             dxn = ops.pixlin(dxz, WinT)
             xn = ops.layernorm_fwd(x3, ln_mode, _f32(n1w), _f32(n1b))
-            d_win = ops.pixlin_wgrad(dxz, xn, out=Z["dwin"], dbias=Z["dbin"]).view_as(w_in)
-            dx, d_n1w, d_n1b = ops.layernorm_bwd(x3, dxn, ln_mode, _f32(n1w), zeroed=(Z["n1w"], Z["n1b"]))
+            (g_win, k_win), (g_bin, k_bin) = _acc(w_in, Z["dwin"]), _acc(b_in, Z["dbin"])
+            d_win = ops.pixlin_wgrad(dxz, xn, out=g_win, dbias=g_bin).view_as(w_in)
+            (g_n1w, k_n1w), (g_n1b, k_n1b) = _acc(n1w, Z["n1w"]), _acc(n1b, Z["n1b"])
+            dx, d_n1w, d_n1b = ops.layernorm_bwd(x3, dxn, ln_mode, _f32(n1w), zeroed=(g_n1w, g_n1b))
             dA_logs = dA * A  # A = -exp(A_logs)
-        return (dx.view(B, C, H, W), d_n1w, d_n1b, d_win, Z["dbin"], d_cw.view_as(cw), d_cb, d_xproj, d_dtw, dbias.view_as(dt_b),
-                dA_logs, dD, d_onw, d_onb, None, None, None, None, None, None)
+        drop = lambda t, direct: None if direct else t  # accumulated straight into .grad: nothing for autograd to add
+        return (dx.view(B, C, H, W), drop(d_n1w, k_n1w), drop(d_n1b, k_n1b), drop(d_win, k_win), drop(g_bin, k_bin),
+                drop(d_cw.view_as(cw), k_cw), drop(d_cb, k_cb), d_xproj, d_dtw, drop(dbias.view_as(dt_b), k_dbias),
+                dA_logs, drop(dD, k_dD), drop(d_onw, k_onw), drop(d_onb, k_onb), None, None, None, None, None, None)
 
 
 class _Tail(torch.autograd.Function):
@@ -200,26 +229,33 @@ class _Tail(torch.autograd.Function):
             dout3 = dout.to(dt_).contiguous().view(B, C, L)
             # project_out
             dgg = ops.pixlin(dout3, WpoutT)
-            d_wpout = ops.pixlin_wgrad(dout3, gg, out=Z["wpout"], dbias=Z["bpout"] if b_pout is not None else None).view_as(w_pout)
+            (g_wpout, k_wpout), (g_bpout, k_bpout) = _acc(w_pout, Z["wpout"]), _acc(b_pout, Z["bpout"])
+            d_wpout = ops.pixlin_wgrad(dout3, gg, out=g_wpout, dbias=g_bpout if b_pout is not None else None).view_as(w_pout)
             # depthwise conv + GELU gate
-            dv, d_fdw, d_fdwb = ops.dwconv3x3_bwd(t, _f32(fdw.view(2 * h, 9)), _f32(fdwb), dgg, h, H, W, 1, zeroed=(Z["fdw"], Z["fdwb"]))
+            (g_fdw, k_fdw), (g_fdwb, k_fdwb) = _acc(fdw, Z["fdw"]), _acc(fdwb, Z["fdwb"])
+            dv, d_fdw, d_fdwb = ops.dwconv3x3_bwd(t, _f32(fdw.view(2 * h, 9)), _f32(fdwb), dgg, h, H, W, 1, zeroed=(g_fdw, g_fdwb))
             dt = ops.dwconv3x3(dv, fdwf, None, 2 * h, H, W, 2)
             # project_in + norm2 (+ the residual branch of the EFFN)
             dx1n = ops.pixlin(dt, WpinT)
             x1n = ops.layernorm_fwd(x1, ln_mode, _f32(n2w), _f32(n2b))
-            d_wpin = ops.pixlin_wgrad(dt, x1n, out=Z["wpin"], dbias=Z["bpin"] if b_pin is not None else None).view_as(w_pin)
-            dx1, d_n2w, d_n2b = ops.layernorm_bwd(x1, dx1n, ln_mode, _f32(n2w), add=dout3, zeroed=(Z["n2w"], Z["n2b"]))
+            (g_wpin, k_wpin), (g_bpin, k_bpin) = _acc(w_pin, Z["wpin"]), _acc(b_pin, Z["bpin"])
+            d_wpin = ops.pixlin_wgrad(dt, x1n, out=g_wpin, dbias=g_bpin if b_pin is not None else None).view_as(w_pin)
+            (g_n2w, k_n2w), (g_n2b, k_n2b) = _acc(n2w, Z["n2w"]), _acc(n2b, Z["n2b"])
+            dx1, d_n2w, d_n2b = ops.layernorm_bwd(x1, dx1n, ln_mode, _f32(n2w), add=dout3, zeroed=(g_n2w, g_n2b))
             # out_conv with the channel gate in front, residual behind
             dyg = ops.pixlin(dx1, WoutT)
             dy2, dc = ops.channel_gate_bwd(dyg, y23, cg, gate_mode)
-            wb = ops.pixlin_wgrad(dx1, y23, per_batch=True, out=Z["wb"], dbias=Z["bout"])  # (B, C_out, C_in): scaled per image by the gate
+            g_bout, k_bout = _acc(b_out, Z["bout"])
+            wb = ops.pixlin_wgrad(dx1, y23, per_batch=True, out=Z["wb"], dbias=g_bout)  # (B, C_out, C_in): scaled per image by the gate
             if gate_mode == 1:
                 d_wout = (wb * (1.0 + cg)[:, None, :]).sum(0)
             else:  # y + c: the gate adds c[b,k] * sum_p dx1[b,m,p]  (per-image row sums: B*C values)
                 d_wout = wb.sum(0) + torch.einsum("bm,bk->mk", dx1.float().sum(2), cg)
-        return (dy2.view(B, C, H, W), dc, dx1.view(B, C, H, W), d_wout.view_as(w_out), Z["bout"] if b_out is not None else None,
-                d_n2w, d_n2b, d_wpin, Z["bpin"] if b_pin is not None else None, d_fdw.view_as(fdw), d_fdwb, d_wpout,
-                Z["bpout"] if b_pout is not None else None, None, None, None, None, None, None, None, None)
+        drop = lambda t, direct: None if direct else t
+        return (dy2.view(B, C, H, W), dc, dx1.view(B, C, H, W), d_wout.view_as(w_out), drop(g_bout, k_bout) if b_out is not None else None,
+                drop(d_n2w, k_n2w), drop(d_n2b, k_n2b), drop(d_wpin, k_wpin), drop(g_bpin, k_bpin) if b_pin is not None else None,
+                drop(d_fdw.view_as(fdw), k_fdw), drop(d_fdwb, k_fdwb), drop(d_wpout, k_wpout),
+                drop(g_bpout, k_bpout) if b_pout is not None else None, None, None, None, None, None, None, None, None)
 
 
 class _Channel(torch.autograd.Function):
@@ -232,6 +268,7 @@ class _Channel(torch.autograd.Function):
                    cout_b=_f32(cout_b), cn_w=_f32(cn_w), cn_b=_f32(cn_b), dc=dc, Rc=Rc, N=N)
         pooled = pooled.detach().float().contiguous()
         ctx.prm, ctx.inv_count, ctx.C = prm, inv_count, C
+        ctx.params = (cin_w, cin_b, xc_proj, dtc_w, dtc_b, Ac_logs, Dsc, cout_w, cout_b, cn_w, cn_b)  # leaves: their .grad is the accumulator
         ctx.save_for_backward(pooled)
         ctx.shapes = [None if t is None else t.shape for t in (cin_w, cin_b, xc_proj, dtc_w, dtc_b, Ac_logs, Dsc, cout_w, cout_b, cn_w, cn_b)]
         return ops.channel_branch(pooled, inv_count, prm, C)
@@ -239,9 +276,15 @@ class _Channel(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dc_out):
         (pooled,) = ctx.saved_tensors
-        dpooled, g = ops.channel_branch_bwd(pooled, ctx.inv_count, ctx.prm, ctx.C, dc_out)
         keys = ("cin_w", "cin_b", "xc_proj", "dtc_w", "dtc_b", "Ac_logs", "Dsc", "cout_w", "cout_b", "cn_w", "cn_b")
-        grads = [None if shp is None else g[k].view(shp) for k, shp in zip(keys, ctx.shapes)]
+        into = {}
+        if _DIRECT_GRADS and not torch.is_grad_enabled():
+            for k, prm in zip(keys, ctx.params):
+                g = getattr(prm, "grad", None) if prm is not None else None
+                if g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.device == pooled.device:
+                    into[k] = g.view(-1)
+        dpooled, g = ops.channel_branch_bwd(pooled, ctx.inv_count, ctx.prm, ctx.C, dc_out, into=into)
+        grads = [None if (shp is None or k in into) else g[k].view(shp) for k, shp in zip(keys, ctx.shapes)]
         return (dpooled, None, None, None, None, None, *grads)
 
 

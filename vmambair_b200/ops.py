@@ -355,7 +355,8 @@ def channel_gate_bwd(dyg, y2, gate, mode):
 def pixlin_wgrad(dy, x, per_batch=False, out=None, dbias=None):
     """dW[m,k] = sum_{b,p} dy[b,m,p] x[b,k,p] -> fp32 (M,K)  (or (B,M,K) without the batch sum).  16-bit activations with 16 B aligned
     rows run this library's mma.sync split-pixel kernel; fp32 (parity mode) or unaligned rows go to the library GEMM.
-    out: optional pre-zeroed fp32 result buffer; dbias: optional pre-zeroed (M) fp32 buffer receiving sum_{b,p} dy (the bias gradient)."""
+    out: optional fp32 accumulator (the result is ADDED: pre-zero it for a plain result); dbias: optional (M) fp32 accumulator receiving
+    sum_{b,p} dy (the bias gradient)."""
     B, M, L = dy.shape
     K = x.shape[1]
     ok = (dy.dtype in (torch.bfloat16, torch.float16) and x.dtype == dy.dtype and dy.stride(2) == 1 and x.stride(2) == 1
@@ -367,7 +368,7 @@ def pixlin_wgrad(dy, x, per_batch=False, out=None, dbias=None):
             dbias += dy.float().sum((0, 2))
         res = wb if per_batch else wb.sum(0)
         if out is not None:
-            out.copy_(res)
+            out.add_(res)  # same contract as the kernel: ADD into the (pre-zeroed or accumulating) buffer
             return out
         return res
     if out is None:
@@ -413,19 +414,26 @@ def channel_branch_bwd_supported(C_, prm) -> bool:
         _lib.lib().vmb_channel_branch_bwd_smem_bytes(C_, prm["dc"], prm["Rc"], prm["N"]) <= 227 * 1024
 
 
-def channel_branch_bwd(pooled, inv_count, prm, C_, dc_out):
-    """backward of channel_branch: -> (dpooled (B,C) fp32, dict of fp32 parameter gradients keyed like prm)"""
+def channel_branch_bwd(pooled, inv_count, prm, C_, dc_out, into=None):
+    """backward of channel_branch: -> (dpooled (B,C) fp32, dict of fp32 parameter gradients keyed like prm).
+    into: optional {key: contiguous fp32 accumulator} -- those gradients are ADDED there (e.g. the parameters' .grad buffers)"""
     B = pooled.shape[0]
     dev = pooled.device
     dc, Rc, N = prm["dc"], prm["Rc"], prm["N"]
     RN = Rc + 2 * N
     sizes = dict(cin_w=dc, cin_b=dc, xc_proj=2 * RN * dc, dtc_w=2 * dc * Rc, dtc_b=2 * dc, Ac_logs=2 * dc * N, Dsc=2 * dc, cout_w=dc,
                  cout_b=1, cn_w=C_, cn_b=C_)
-    flat = torch.zeros(sum(sizes.values()), dtype=torch.float32, device=dev)  # one zero fill for every accumulator
+    into = into or {}
+    own = {k: n for k, n in sizes.items() if k not in into}
     g, o = {}, 0
-    for k, n in sizes.items():
-        g[k] = flat[o:o + n]
-        o += n
+    if own:
+        flat = torch.zeros(sum(own.values()), dtype=torch.float32, device=dev)  # one zero fill for every accumulator
+        for k, n in own.items():
+            g[k] = flat[o:o + n]
+            o += n
+    for k, t in into.items():
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == sizes[k]
+        g[k] = t
     has_cin, has_cout = prm["cin_w"] is not None, prm["cout_w"] is not None
     dpooled = torch.empty((B, C_), dtype=torch.float32, device=dev)
     scratch = torch.empty(_lib.lib().vmb_channel_branch_bwd_scratch_bytes(B, dc, C_) // 4, dtype=torch.float32, device=dev)

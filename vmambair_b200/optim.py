@@ -39,6 +39,10 @@ class FlatAdam:
         self.ema = self.flat_param.clone() if ema_decay > 0 else None
         self.lr, self.betas, self.eps, self.weight_decay, self.decoupled = lr, betas, eps, weight_decay, decoupled
         self.ema_decay, self.max_grad_norm = ema_decay, max_grad_norm
+        # the .grad views exist from here on: let the fused backward kernels add into them directly (no AccumulateGrad launch per
+        # parameter -- ~1 500 tiny kernels per step on the full SR net)
+        from . import fused_train
+        fused_train.set_direct_grads(True)
 
     def check_views(self):
         """.grad must still alias the flat buffer (zero_grad(set_to_none=True) would break it)"""
