@@ -96,6 +96,60 @@ def test_direct_grad_accumulation_equals_autograd_accumulation(variant, dim):
     assert all(float(g.abs().max()) > 0 for n, g in zip(names, res[True]) if not n.endswith("conv_cout.bias")), "a gradient stayed zero"
 
 
+def test_side_stream_weight_gradients_equal_single_stream_on_a_net():
+    """the weight-gradient kernels on the second stream (fused_train._Side) vs everything on one stream: a 4-level net with FlatAdam's
+    flat gradient buffer, bf16 autocast, eager and replayed from a CUDA graph -- same flat gradient up to the fp32 atomics' order"""
+    import torch.nn.functional as F
+    from vmambair_b200 import fused_train
+    from vmambair_b200.optim import FlatAdam
+    torch.manual_seed(11)
+    archs.set_train_path("fused")
+    net = archs.MambaSISR6(dim=16, num_blocks=[2, 1, 1, 1], num_refinement_blocks=2).cuda().train()
+    opt = FlatAdam(net.parameters(), lr=1e-4)
+    lq, gt = torch.rand(2, 3, 32, 32, device="cuda"), torch.rand(2, 3, 128, 128, device="cuda")
+
+    def fwd_bwd():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = net(lq)
+        loss = F.l1_loss(out.float(), gt)
+        loss.backward()
+        return loss
+
+    res = {}
+    try:
+        for side in (False, True):
+            fused_train._Side.on = side
+            opt.flat_grad.zero_()
+            fwd_bwd()
+            torch.cuda.synchronize()
+            res[side] = opt.flat_grad.clone()
+        assert float(res[False].abs().max()) > 0
+        rel = float((res[True] - res[False]).norm() / res[False].norm())
+        assert rel < 1e-3, rel  # bf16 activations: the only difference is the order of fp32 atomic adds
+        # CUDA-graph capture of the forked / joined backward
+        fused_train._Side.on = True
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            opt.flat_grad.zero_()
+            fwd_bwd()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        opt.check_views()
+        opt.flat_grad.zero_()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fwd_bwd()
+        opt.flat_grad.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        rel = float((opt.flat_grad - res[False]).norm() / res[False].norm())
+        assert rel < 1e-3, rel
+    finally:
+        fused_train._Side.on = True
+        fused_train.set_direct_grads(False)
+
+
 def test_block_fused_training_bf16_close_to_fp32():
     """bf16 activations / fp32 parameters (the autocast training configuration): gradients within bf16 noise of the fp32 run"""
     torch.manual_seed(5)

@@ -24,6 +24,9 @@ gradients.  fp32 activations (parity mode) send the weight gradients to the libr
 """
 from __future__ import annotations
 
+import contextlib
+import os
+
 import torch
 
 from . import ops
@@ -47,6 +50,48 @@ def _acc(param, fallback):
             g.numel() == fallback.numel() and not torch.is_grad_enabled():
         return g.view(fallback.shape), True
     return fallback, False
+
+
+class _Side:
+    """Second stream for the weight-gradient kernels of the backward pass.  Nothing downstream of a block waits for its weight
+    gradients (with direct .grad accumulation not even autograd does), while the data-gradient chain is a sequence of small-grid,
+    latency-bound launches at the training batch (4 images): the wgrad GEMMs and LayerNorm recomputations run beside it
+    (fork: side waits for the current stream; join: one wait at the end of the backward pass, queued as an autograd callback --
+    also under CUDA-graph capture, where this becomes a fork / join of graph branches)."""
+    stream = {}      # device index -> torch.cuda.Stream
+    keep = []        # tensors the side-stream kernels read: kept alive until the join
+    armed = False
+    on = os.environ.get("VMB_TRAIN_SIDE", "1") == "1"
+
+
+def join_side_stream():
+    """make the current stream wait for the weight-gradient stream (idempotent; optim.FlatAdam.step calls it before it reads .grad)"""
+    _side_join()
+
+
+def _side_join():
+    _Side.armed = False
+    for st in _Side.stream.values():
+        torch.cuda.current_stream(st.device).wait_stream(st)
+    _Side.keep.clear()
+
+
+@contextlib.contextmanager
+def _side(ok, dev, *keep):
+    """run the enclosed launches on the side stream when `ok` (their results go nowhere but into .grad buffers)"""
+    if not (ok and _Side.on and _DIRECT_GRADS and not torch.is_grad_enabled()):
+        yield False
+        return
+    st = _Side.stream.get(dev.index)
+    if st is None:
+        st = _Side.stream[dev.index] = torch.cuda.Stream(dev)
+    if not _Side.armed:
+        torch.autograd.Variable._execution_engine.queue_callback(_side_join)
+        _Side.armed = True
+    _Side.keep.extend(keep)
+    st.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(st):
+        yield True
 
 
 _DIRECT_GRADS = False  # opt-in (optim.FlatAdam turns it on): only valid for .backward()-style accumulation into .grad
@@ -172,19 +217,27 @@ class _Front(torch.autograd.Function):
             ops.cross_scan([dC[:, k] for k in range(4)], N, W, H, out=ddbl[:, :, C + N:])
             ddbl = ddbl.view(B, Mb, L)
             dxc = ops.sum4_add(dxc4, ops.pixlin(ddbl, WbigT))  # x_proj data gradient + the four direction gradients of u
-            dbig = ops.pixlin_wgrad(ddbl, xc, out=Z["dbig"]).view(4, C + 2 * N, C)
             xw, dtw = x_proj_w.detach(), dt_w.detach()
-            d_xproj = torch.cat([torch.bmm(dtw.transpose(1, 2), dbig[:, :C]), dbig[:, C:]], 1)  # [W_dt^T dW ; dW[C:]]
-            d_dtw = torch.bmm(dbig[:, :C], xw[:, :R].transpose(1, 2))                            # dW W_x[:R]^T
+            gx, gd = getattr(x_proj_w, "grad", None), getattr(dt_w, "grad", None)
+            k_big = _DIRECT_GRADS and gx is not None and gd is not None and gx.dtype == gd.dtype == torch.float32 and not torch.is_grad_enabled()
+            with _side(k_big, dev, ddbl, xc, Z["dbig"]):
+                dbig = ops.pixlin_wgrad(ddbl, xc, out=Z["dbig"]).view(4, C + 2 * N, C)
+                d_xproj = torch.cat([torch.bmm(dtw.transpose(1, 2), dbig[:, :C]), dbig[:, C:]], 1)  # [W_dt^T dW ; dW[C:]]
+                d_dtw = torch.bmm(dbig[:, :C], xw[:, :R].transpose(1, 2))                            # dW W_x[:R]^T
+                if k_big:
+                    gx.add_(d_xproj)
+                    gd.add_(d_dtw)
+                    d_xproj = d_dtw = None
             # depthwise conv + SiLU
             (g_cw, k_cw), (g_cb, k_cb) = _acc(cw, Z["dcw"]), _acc(cb, Z["dcb"])
             dv, d_cw, d_cb = ops.dwconv3x3_bwd(xz[:, :C], _f32(cw.view(C, 9)), _f32(cb), dxc, C, H, W, 0, zeroed=(g_cw, g_cb))
             ops.dwconv3x3(dv, cwf, None, C, H, W, 2, out=dxz[:, :C])
             # in_conv + norm1
             dxn = ops.pixlin(dxz, WinT)
-            xn = ops.layernorm_fwd(x3, ln_mode, _f32(n1w), _f32(n1b))
             (g_win, k_win), (g_bin, k_bin) = _acc(w_in, Z["dwin"]), _acc(b_in, Z["dbin"])
-            d_win = ops.pixlin_wgrad(dxz, xn, out=g_win, dbias=g_bin).view_as(w_in)
+            with _side(k_win and (b_in is None or k_bin), dev, x3, dxz):
+                xn = ops.layernorm_fwd(x3, ln_mode, _f32(n1w), _f32(n1b))
+                d_win = ops.pixlin_wgrad(dxz, xn, out=g_win, dbias=g_bin).view_as(w_in)
             (g_n1w, k_n1w), (g_n1b, k_n1b) = _acc(n1w, Z["n1w"]), _acc(n1b, Z["n1b"])
             dx, d_n1w, d_n1b = ops.layernorm_bwd(x3, dxn, ln_mode, _f32(n1w), zeroed=(g_n1w, g_n1b))
             dA_logs = dA * A  # A = -exp(A_logs)
@@ -230,29 +283,37 @@ class _Tail(torch.autograd.Function):
             # project_out
             dgg = ops.pixlin(dout3, WpoutT)
             (g_wpout, k_wpout), (g_bpout, k_bpout) = _acc(w_pout, Z["wpout"]), _acc(b_pout, Z["bpout"])
-            d_wpout = ops.pixlin_wgrad(dout3, gg, out=g_wpout, dbias=g_bpout if b_pout is not None else None).view_as(w_pout)
+            with _side(k_wpout and (b_pout is None or k_bpout), dev, dout3, gg):
+                d_wpout = ops.pixlin_wgrad(dout3, gg, out=g_wpout, dbias=g_bpout if b_pout is not None else None).view_as(w_pout)
             # depthwise conv + GELU gate
             (g_fdw, k_fdw), (g_fdwb, k_fdwb) = _acc(fdw, Z["fdw"]), _acc(fdwb, Z["fdwb"])
             dv, d_fdw, d_fdwb = ops.dwconv3x3_bwd(t, _f32(fdw.view(2 * h, 9)), _f32(fdwb), dgg, h, H, W, 1, zeroed=(g_fdw, g_fdwb))
             dt = ops.dwconv3x3(dv, fdwf, None, 2 * h, H, W, 2)
             # project_in + norm2 (+ the residual branch of the EFFN)
             dx1n = ops.pixlin(dt, WpinT)
-            x1n = ops.layernorm_fwd(x1, ln_mode, _f32(n2w), _f32(n2b))
             (g_wpin, k_wpin), (g_bpin, k_bpin) = _acc(w_pin, Z["wpin"]), _acc(b_pin, Z["bpin"])
-            d_wpin = ops.pixlin_wgrad(dt, x1n, out=g_wpin, dbias=g_bpin if b_pin is not None else None).view_as(w_pin)
+            with _side(k_wpin and (b_pin is None or k_bpin), dev, x1, dt):
+                x1n = ops.layernorm_fwd(x1, ln_mode, _f32(n2w), _f32(n2b))
+                d_wpin = ops.pixlin_wgrad(dt, x1n, out=g_wpin, dbias=g_bpin if b_pin is not None else None).view_as(w_pin)
             (g_n2w, k_n2w), (g_n2b, k_n2b) = _acc(n2w, Z["n2w"]), _acc(n2b, Z["n2b"])
             dx1, d_n2w, d_n2b = ops.layernorm_bwd(x1, dx1n, ln_mode, _f32(n2w), add=dout3, zeroed=(g_n2w, g_n2b))
             # out_conv with the channel gate in front, residual behind
             dyg = ops.pixlin(dx1, WoutT)
             dy2, dc = ops.channel_gate_bwd(dyg, y23, cg, gate_mode)
             g_bout, k_bout = _acc(b_out, Z["bout"])
-            wb = ops.pixlin_wgrad(dx1, y23, per_batch=True, out=Z["wb"], dbias=g_bout)  # (B, C_out, C_in): scaled per image by the gate
-            if gate_mode == 1:
-                d_wout = (wb * (1.0 + cg)[:, None, :]).sum(0)
-            else:  # y + c: the gate adds c[b,k] * sum_p dx1[b,m,p]  (per-image row sums: B*C values)
-                d_wout = wb.sum(0) + torch.einsum("bm,bk->mk", dx1.float().sum(2), cg)
+            g_wout = getattr(w_out, "grad", None)
+            k_wout = _DIRECT_GRADS and g_wout is not None and g_wout.dtype == torch.float32 and not torch.is_grad_enabled()
+            with _side(k_wout and (b_out is None or k_bout), dev, dx1, y23, cg, Z["wb"]):
+                wb = ops.pixlin_wgrad(dx1, y23, per_batch=True, out=Z["wb"], dbias=g_bout)  # (B, C_out, C_in): scaled per image by the gate
+                if gate_mode == 1:
+                    d_wout = (wb * (1.0 + cg)[:, None, :]).sum(0)
+                else:  # y + c: the gate adds c[b,k] * sum_p dx1[b,m,p]  (per-image row sums: B*C values)
+                    d_wout = wb.sum(0) + torch.einsum("bm,bk->mk", dx1.float().sum(2), cg)
+                if k_wout:
+                    g_wout.add_(d_wout.view_as(g_wout))
+                    d_wout = None
         drop = lambda t, direct: None if direct else t
-        return (dy2.view(B, C, H, W), dc, dx1.view(B, C, H, W), d_wout.view_as(w_out), drop(g_bout, k_bout) if b_out is not None else None,
+        return (dy2.view(B, C, H, W), dc, dx1.view(B, C, H, W), None if d_wout is None else d_wout.view_as(w_out), drop(g_bout, k_bout) if b_out is not None else None,
                 drop(d_n2w, k_n2w), drop(d_n2b, k_n2b), drop(d_wpin, k_wpin), drop(g_bpin, k_bpin) if b_pin is not None else None,
                 drop(d_fdw.view_as(fdw), k_fdw), drop(d_fdwb, k_fdwb), drop(d_wpout, k_wpout),
                 drop(g_bpout, k_bpout) if b_pout is not None else None, None, None, None, None, None, None, None, None)

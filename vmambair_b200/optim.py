@@ -54,6 +54,8 @@ class FlatAdam:
 
     @torch.no_grad()
     def step(self, grad_scale: float = 1.0, zero_grad: bool = True):
+        from . import fused_train
+        fused_train.join_side_stream()  # normally already joined by the end-of-backward callback
         a = _lib.AdamArgs(self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                           self.ema.data_ptr() if self.ema is not None else None, self.state.data_ptr(), self.n,
                           self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, int(self.decoupled),
