@@ -118,6 +118,9 @@ typedef struct {
     int64_t x_bs, x_cs, r_bs, r_cs, o_bs, o_cs, g_bs;
     int64_t w_ld;                           /* row stride of w (0: = K); rows padded to a multiple of 16 elements load vectorised */
     int dtype, out_dtype;                   /* x / w / residual dtype; out dtype (same, or VMB_F32) */
+    int w_static;                           /* 1: w / bias / ln_w / ln_b were final before the preceding kernel of the stream was launched
+                                             * (cached inference weights): the kernel may stage them while that kernel still runs
+                                             * (programmatic dependent launch); 0: they may be its output -- fetched after it completes */
 } vmb_pixlin_args;
 int vmb_pixlin(const vmb_pixlin_args* a, void* stream);
 
@@ -199,7 +202,8 @@ typedef struct {
 int vmb_layernorm_fwd(const vmb_ln_fwd_args* a, void* stream);
 
 /* dx = LayerNorm backward of g (gradient w.r.t. the LayerNorm output) [+ add]; dw += sum g*xhat, db += sum g (dw/db may be NULL).
- * stats: fp32 scratch (B, L, 2), written. */
+ * stats: fp32 scratch (B, L, 2), written by the data-gradient kernel.  Two-phase use (weight gradients on another stream):
+ * dw = NULL -> dx (+ stats) only; dx = NULL -> dw / db only, from x, g and the stats of the earlier call. */
 typedef struct {
     const void* x; const void* g; const void* add; const float* w; void* dx; float* dw; float* db; float* stats;
     int batch, C, L, mode;
@@ -211,7 +215,8 @@ int vmb_layernorm_bwd(const vmb_ln_bwd_args* a, void* stream);
 /* backward of vmb_merge_norm_gate (z_preact = 1): merged / stats = the forward's workspace (fp32 merged scan output (B,C,L) and the
  * per-pixel (sum, sum of squares) over C); dy2 (B,C,L) dense, dpooled (B,C) fp32 or NULL.
  * -> dm (B,C,L) dense: gradient w.r.t. the merged scan output (gathered into the four scan orders by vmb_cross_scan),
- *    dz: gradient w.r.t. the pre-activation z, dw/db += out_norm parameter gradients. */
+ *    dz: gradient w.r.t. the pre-activation z, dw/db += out_norm parameter gradients.
+ * Two-phase use: dw = db = NULL -> data gradients only; dm = dz = NULL -> parameter gradients only. */
 typedef struct {
     const float* merged; const float* stats; const void* z; const void* dy2; const float* dpooled;
     const float* w; const float* b; void* dm; void* dz; float* dw; float* db;
@@ -223,7 +228,8 @@ int vmb_merge_norm_gate_bwd(const vmb_merge_bwd_args* a, void* stream);
 
 /* backward of vmb_dwconv3x3 up to the conv output: dv = gradient w.r.t. the conv result before the activation
  * (mode 0: g * silu'(v); mode 1: dv[c] = g * v2 * gelu'(v1), dv[c+c_out] = g * gelu(v1)); the conv itself is recomputed from x.
- * dw (channels, 9) / dbias (channels) fp32 accumulated when dw != NULL.  The input gradient is vmb_dwconv3x3(dv, flipped taps, mode 2). */
+ * dw (channels, 9) / dbias (channels) fp32 accumulated when dw != NULL.  The input gradient is vmb_dwconv3x3(dv, flipped taps, mode 2).
+ * Two-phase use: dw = NULL -> dv only; g = NULL -> dv is an INPUT (an earlier call's) and only dw / dbias are accumulated. */
 typedef struct {
     const void* x; const float* w; const float* bias; const void* g; void* dv; float* dw; float* dbias;
     int batch, c_out, H, W, mode;

@@ -96,9 +96,13 @@ def test_direct_grad_accumulation_equals_autograd_accumulation(variant, dim):
     assert all(float(g.abs().max()) > 0 for n, g in zip(names, res[True]) if not n.endswith("conv_cout.bias")), "a gradient stayed zero"
 
 
-def test_side_stream_weight_gradients_equal_single_stream_on_a_net():
+@pytest.mark.parametrize("amp", [False, True])
+def test_side_stream_weight_gradients_equal_single_stream_on_a_net(amp):
     """the weight-gradient kernels on the second stream (fused_train._Side) vs everything on one stream: a 4-level net with FlatAdam's
-    flat gradient buffer, bf16 autocast, eager and replayed from a CUDA graph -- same flat gradient up to the fp32 atomics' order"""
+    flat gradient buffer, eager and replayed from a CUDA graph.  fp32 activations: only the order of the fp32 atomic adds differs
+    (1e-4); bf16 autocast: the forward itself is reproducible only up to bf16 rounding flips behind the out_norm statistics'
+    atomics (tools/side_debug.py: 0 ... 2e-3 on the output, 2e-3 ... 1e-2 on the gradients between identical single-stream runs),
+    so that case only guards against gross errors (a missing or doubled weight gradient is O(1))."""
     import torch.nn.functional as F
     from vmambair_b200 import fused_train
     from vmambair_b200.optim import FlatAdam
@@ -107,14 +111,16 @@ def test_side_stream_weight_gradients_equal_single_stream_on_a_net():
     net = archs.MambaSISR6(dim=16, num_blocks=[2, 1, 1, 1], num_refinement_blocks=2).cuda().train()
     opt = FlatAdam(net.parameters(), lr=1e-4)
     lq, gt = torch.rand(2, 3, 32, 32, device="cuda"), torch.rand(2, 3, 128, 128, device="cuda")
+    tol = 5e-2 if amp else 1e-4
 
     def fwd_bwd():
-        with torch.autocast("cuda", dtype=torch.bfloat16):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
             out = net(lq)
         loss = F.l1_loss(out.float(), gt)
         loss.backward()
         return loss
 
+    dist = lambda a, b: float((a - b).norm() / b.norm())
     res = {}
     try:
         for side in (False, True):
@@ -124,8 +130,7 @@ def test_side_stream_weight_gradients_equal_single_stream_on_a_net():
             torch.cuda.synchronize()
             res[side] = opt.flat_grad.clone()
         assert float(res[False].abs().max()) > 0
-        rel = float((res[True] - res[False]).norm() / res[False].norm())
-        assert rel < 1e-3, rel  # bf16 activations: the only difference is the order of fp32 atomic adds
+        assert dist(res[True], res[False]) <= tol, dist(res[True], res[False])
         # CUDA-graph capture of the forked / joined backward
         fused_train._Side.on = True
         s = torch.cuda.Stream()
@@ -140,11 +145,11 @@ def test_side_stream_weight_gradients_equal_single_stream_on_a_net():
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             fwd_bwd()
-        opt.flat_grad.zero_()
-        g.replay()
-        torch.cuda.synchronize()
-        rel = float((opt.flat_grad - res[False]).norm() / res[False].norm())
-        assert rel < 1e-3, rel
+        for _ in range(2):
+            opt.flat_grad.zero_()
+            g.replay()
+            torch.cuda.synchronize()
+            assert dist(opt.flat_grad, res[False]) <= tol, dist(opt.flat_grad, res[False])
     finally:
         fused_train._Side.on = True
         fused_train.set_direct_grads(False)

@@ -11,6 +11,7 @@ struct PixlinParams {
     int64_t x_bs, x_cs, r_bs, r_cs, o_bs, o_cs, g_bs, w_ld;
     bool vec_ok, w_vec, w_all;
     int w_tiles;  // weight-tile buffers in smem (2 = double buffer, or every tile of the CTA when w_all)
+    int w_static; // weights / parameters may be fetched before griddepcontrol.wait (not produced by the preceding kernel)
 };
 struct DwParams {
     const void* x; const float* w; const float* bias; void* out;

@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pixlin_tc_kernel(const PixlinPa
                                                                   const int trace, const int backoff) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     pdl_trigger();  // everything up to pdl_wait() below touches only weights / parameters and this CTA's own state
+    if (!p.w_static) pdl_wait();  // training: the weights are the preceding kernel's output (vmb_prep_block_weights)
     long long* tr = (trace && blockIdx.x < 160) ? g_tc_trace + blockIdx.x * 64 : nullptr;
     if (tr && threadIdx.x == 0) tr[0] = gtimer();
     const int kpad = (p.K + 15) / 16 * 16;

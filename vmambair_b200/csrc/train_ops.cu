@@ -727,6 +727,11 @@ int ln_fwd_launch(const LnFwdParams& p, int dtype, cudaStream_t stream) {
 
 int ln_bwd_launch(const LnBwdParams& p, int dtype, cudaStream_t stream) {
     VMB_CHECK(p.B <= 65535 && p.C <= 65535, "layernorm_bwd: batch / channels > 65535");
+    if (!p.dx) {  // parameter gradients only (the statistics of an earlier data-gradient call)
+        VMB_DISPATCH(dtype, ln_bwd_dwdb_kernel, dim3(p.C, p.B), dim3(256), p);
+        VMB_CUDA(cudaGetLastError());
+        return VMB_OK;
+    }
     if (p.L >= 2 && even(p.L) && even(p.x_bs) && even(p.x_cs) && even(p.g_bs) && even(p.g_cs) && even(p.a_bs) && even(p.a_cs) && even(p.dx_bs) &&
         even(p.dx_cs) && al8(p.x) && al8(p.g) && al8(p.dx) && (!p.add || al8(p.add)) && p.C >= PX_Q) {
         VMB_DISPATCH(dtype, ln_bwd_dx_px_kernel, dim3((p.L / 2 + PX_PAIRS - 1) / PX_PAIRS, p.B), dim3(256), p);
@@ -739,12 +744,17 @@ int ln_bwd_launch(const LnBwdParams& p, int dtype, cudaStream_t stream) {
 
 int merge_bwd_launch(const MergeBwdParams& p, int dtype, cudaStream_t stream) {
     VMB_CHECK(p.B <= 65535 && p.C <= 65535, "merge_bwd: batch / channels > 65535");
+    if (!p.dm) {  // parameter gradients only
+        VMB_DISPATCH(dtype, merge_bwd_dwdb_kernel, dim3(p.C, p.B), dim3(256), p);
+        VMB_CUDA(cudaGetLastError());
+        return VMB_OK;
+    }
     if (p.L >= 2 && even(p.L) && even(p.z_bs) && even(p.z_cs) && even(p.dz_bs) && even(p.dz_cs) && al8(p.z) && al8(p.dz) && al8(p.dy2) &&
         al8(p.dm) && (reinterpret_cast<uintptr_t>(p.stats) & 15) == 0 && p.C >= PX_Q) {
         VMB_DISPATCH(dtype, merge_bwd_dx_px_kernel, dim3((p.L / 2 + PX_PAIRS - 1) / PX_PAIRS, p.B), dim3(256), p);
     } else
     VMB_DISPATCH(dtype, merge_bwd_dx_kernel, dim3((p.L + 127) / 128, p.B), dim3(128), p);
-    VMB_DISPATCH(dtype, merge_bwd_dwdb_kernel, dim3(p.C, p.B), dim3(256), p);
+    if (p.dw) VMB_DISPATCH(dtype, merge_bwd_dwdb_kernel, dim3(p.C, p.B), dim3(256), p);
     VMB_CUDA(cudaGetLastError());
     return VMB_OK;
 }
@@ -789,7 +799,7 @@ extern "C" int vmb_layernorm_fwd(const vmb_ln_fwd_args* a, void* stream) {
 }
 
 extern "C" int vmb_layernorm_bwd(const vmb_ln_bwd_args* a, void* stream) {
-    VMB_CHECK(a && a->x && a->g && a->w && a->dx && a->stats, "layernorm_bwd: null pointer");
+    VMB_CHECK(a && a->x && a->g && a->w && (a->dx || a->dw) && a->stats, "layernorm_bwd: null pointer");
     VMB_CHECK(tdt_ok(a->dtype) && (a->mode == 1 || a->mode == 2), "layernorm_bwd: bad dtype / mode");
     VMB_CHECK(a->batch > 0 && a->C > 0 && a->L > 0, "layernorm_bwd: bad sizes");
     LnBwdParams p{a->x, a->g, a->add, a->w, a->dx, a->dw, a->db, a->stats, a->batch, a->C, a->L, a->mode,
@@ -798,7 +808,9 @@ extern "C" int vmb_layernorm_bwd(const vmb_ln_bwd_args* a, void* stream) {
 }
 
 extern "C" int vmb_merge_norm_gate_bwd(const vmb_merge_bwd_args* a, void* stream) {
-    VMB_CHECK(a && a->merged && a->stats && a->z && a->dy2 && a->w && a->b && a->dm && a->dz && a->dw && a->db, "merge_bwd: null pointer");
+    VMB_CHECK(a && a->merged && a->stats && a->z && a->dy2 && a->w && a->b, "merge_bwd: null pointer");
+    VMB_CHECK((a->dm && a->dz) || (!a->dm && !a->dz && a->dw), "merge_bwd: dm and dz together (data gradients), or neither (parameter gradients only)");
+    VMB_CHECK((a->dw == nullptr) == (a->db == nullptr), "merge_bwd: dw and db together");
     VMB_CHECK(tdt_ok(a->dtype) && a->batch > 0 && a->C > 0 && a->L > 0, "merge_bwd: bad arguments");
     MergeBwdParams p{a->merged, a->stats, a->z, a->dy2, a->dpooled, a->w, a->b, a->dm, a->dz, a->dw, a->db,
                      a->batch, a->C, a->L, a->z_bs, a->z_cs, a->dz_bs, a->dz_cs};
@@ -806,16 +818,17 @@ extern "C" int vmb_merge_norm_gate_bwd(const vmb_merge_bwd_args* a, void* stream
 }
 
 extern "C" int vmb_dwconv3x3_bwd(const vmb_dwconv_bwd_args* a, void* stream) {
-    VMB_CHECK(a && a->x && a->w && a->g && a->dv, "dwconv_bwd: null pointer");
+    VMB_CHECK(a && a->x && a->w && a->dv && (a->g || a->dw), "dwconv_bwd: null pointer");
     VMB_CHECK(tdt_ok(a->dtype) && (a->mode == 0 || a->mode == 1) && a->batch > 0 && a->c_out > 0 && a->H > 0 && a->W > 0, "dwconv_bwd: bad arguments");
     DwBwdParams p{a->x, a->w, a->bias, a->g, a->dv, a->dw, a->dbias, a->batch, a->c_out, a->H, a->W, a->mode,
                   a->x_bs, a->x_cs, a->g_bs, a->g_cs, a->dv_bs, a->dv_cs, false};
     {
         auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-        p.vec_ok = a->W % 8 == 0 && al16(a->x) && al16(a->g) && al16(a->dv) && a->x_bs % 8 == 0 && a->x_cs % 8 == 0 && a->g_bs % 8 == 0 &&
-                   a->g_cs % 8 == 0 && a->dv_bs % 8 == 0 && a->dv_cs % 8 == 0;
+        p.vec_ok = a->W % 8 == 0 && al16(a->x) && (!a->g || al16(a->g)) && al16(a->dv) && a->x_bs % 8 == 0 && a->x_cs % 8 == 0 &&
+                   (!a->g || (a->g_bs % 8 == 0 && a->g_cs % 8 == 0)) && a->dv_bs % 8 == 0 && a->dv_cs % 8 == 0;
     }
-    int rc = dwconv_bwd_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
+    int rc = VMB_OK;
+    if (a->g) rc = dwconv_bwd_launch(p, a->dtype, static_cast<cudaStream_t>(stream));  // g == NULL: dv is an input, weight gradients only
     if (rc != VMB_OK || !a->dw) return rc;
     return dwconv_wgrad_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
 }

@@ -151,10 +151,12 @@ def _run(name, args, t, tag, nbytes=0, kernels=1):
         _lib.check(fn(C.byref(args), _stream(t)), name)
 
 
-def pixlin(x, w, bias=None, residual=None, ln=None, gate=None, gate_mode=0, act=(0, 0), out_dtype=None, out=None):
+def pixlin(x, w, bias=None, residual=None, ln=None, gate=None, gate_mode=0, act=(0, 0), out_dtype=None, out=None, static_w=False):
     """out[b,m,p] = epi(sum_k w[m,k] pro(x)[b,k,p]).  x: (B,K,P) view with stride(-1)==1; w: (M,>=K) x.dtype, rows may be
     zero-padded to a multiple of 16 (pad_weight) for vector loads.
-    ln = (mode, weight_fp32, bias_fp32|None); gate: (B,K) fp32; residual: (B,M,P) view."""
+    ln = (mode, weight_fp32, bias_fp32|None); gate: (B,K) fp32; residual: (B,M,P) view.
+    static_w: w / bias / ln parameters were written long before this call (cached inference weights), so the kernel may fetch them
+    while the preceding kernel of the stream is still running; leave False when they are that kernel's output."""
     B, K, P = x.shape
     M = w.shape[0]
     assert w.shape[1] >= K and w.dtype == x.dtype and w.stride(1) == 1 and x.stride(2) == 1
@@ -167,7 +169,7 @@ def pixlin(x, w, bias=None, residual=None, ln=None, gate=None, gate_mode=0, act=
         ln_mode, gate_mode if gate is not None else 0, act[0], act[1], B, K, M, P,
         x.stride(0), x.stride(1), residual.stride(0) if residual is not None else 0,
         residual.stride(1) if residual is not None else 0, out.stride(0), out.stride(1),
-        gate.stride(0) if gate is not None else 0, w.stride(0), _DT[x.dtype], _DT[out_dtype])
+        gate.stride(0) if gate is not None else 0, w.stride(0), _DT[x.dtype], _DT[out_dtype], int(static_w))
     _run("vmb_pixlin", a, x, "pixlin", 0)
     return out
 
@@ -292,52 +294,84 @@ def layernorm_fwd(x, mode, w, b):
     return y
 
 
-def layernorm_bwd(x, g, mode, w, add=None, need_param_grads=True, zeroed=None):
-    """-> (dx (B,C,L), dw (C) fp32, db (C) fp32 | None): LayerNorm backward of g [+ add] (the residual branch's gradient)."""
+def layernorm_bwd(x, g, mode, w, add=None, need_param_grads=True, zeroed=None, phase="both", stats=None):
+    """-> (dx (B,C,L), dw (C) fp32, db (C) fp32 | None): LayerNorm backward of g [+ add] (the residual branch's gradient).
+    phase "data": dx only -> (dx, stats);  phase "params" (stats of the "data" call): dw / db only -> (dw, db)."""
     B, C_, L = x.shape
     assert x.stride(2) == 1 and g.stride(2) == 1 and g.dtype == x.dtype and (add is None or (add.stride(2) == 1 and add.dtype == x.dtype))
-    dx = torch.empty((B, C_, L), dtype=x.dtype, device=x.device)
-    stats = torch.empty((B, L, 2), dtype=torch.float32, device=x.device)
-    if zeroed is not None:
-        dw, db = zeroed[0], (zeroed[1] if mode == 1 else None)
-    else:
-        dw = torch.zeros(C_, dtype=torch.float32, device=x.device) if need_param_grads else None
-        db = torch.zeros(C_, dtype=torch.float32, device=x.device) if (need_param_grads and mode == 1) else None
+    assert phase in ("both", "data", "params") and (phase != "params" or stats is not None)
+    dx = torch.empty((B, C_, L), dtype=x.dtype, device=x.device) if phase != "params" else None
+    if stats is None:
+        stats = torch.empty((B, L, 2), dtype=torch.float32, device=x.device)
+    dw = db = None
+    if phase != "data":
+        if zeroed is not None:
+            dw, db = zeroed[0], (zeroed[1] if mode == 1 else None)
+        elif need_param_grads:
+            dw = torch.zeros(C_, dtype=torch.float32, device=x.device)
+            db = torch.zeros(C_, dtype=torch.float32, device=x.device) if mode == 1 else None
     a = _lib.LnBwdArgs(_ptr(x), _ptr(g), _ptr(add), _ptr(w), _ptr(dx), _ptr(dw), _ptr(db), _ptr(stats), B, C_, L, mode,
                        x.stride(0), x.stride(1), g.stride(0), g.stride(1), add.stride(0) if add is not None else 0,
-                       add.stride(1) if add is not None else 0, dx.stride(0), dx.stride(1), _DT[x.dtype])
-    _run("vmb_layernorm_bwd", a, x, "ln_bwd", 0, 2 if need_param_grads else 1)
+                       add.stride(1) if add is not None else 0, dx.stride(0) if dx is not None else 0, dx.stride(1) if dx is not None else 0,
+                       _DT[x.dtype])
+    _run("vmb_layernorm_bwd", a, x, "ln_bwd", 0, (1 if dx is not None else 0) + (1 if dw is not None else 0))
+    if phase == "data":
+        return dx, stats
+    if phase == "params":
+        return dw, db
     return dx, dw, db
 
 
-def merge_norm_gate_bwd(ws, z, dy2, dpooled, ln_w, ln_b, C_, L, dz_out, zeroed=None):
+def merge_norm_gate_bwd(ws, z, dy2, dpooled, ln_w, ln_b, C_, L, dz_out, zeroed=None, phase="both"):
     """backward of merge_norm_gate(z_preact=True).  ws: the forward's workspace; dy2 (B,C,L) contiguous; dpooled (B,C) fp32|None;
-    dz_out: (B,C,L) view receiving the gradient w.r.t. the pre-activation z.  -> (dm (B,C,L), d ln_w, d ln_b)."""
+    dz_out: (B,C,L) view receiving the gradient w.r.t. the pre-activation z.  -> (dm (B,C,L), d ln_w, d ln_b).
+    phase "data": -> dm (dz_out written);  phase "params": -> (d ln_w, d ln_b) only."""
     B = dy2.shape[0]
-    assert dy2.is_contiguous() and z.stride(2) == 1 and dz_out.stride(2) == 1
+    assert dy2.is_contiguous() and z.stride(2) == 1 and (dz_out is None or dz_out.stride(2) == 1) and phase in ("both", "data", "params")
     merged = ws.view(torch.float32)
     stats = merged[B * C_ * L:]
-    dm = torch.empty((B, C_, L), dtype=dy2.dtype, device=dy2.device)
-    dw = torch.zeros(C_, dtype=torch.float32, device=dy2.device) if zeroed is None else zeroed[0]
-    db = torch.zeros(C_, dtype=torch.float32, device=dy2.device) if zeroed is None else zeroed[1]
-    a = _lib.MergeBwdArgs(_ptr(merged), _ptr(stats), _ptr(z), _ptr(dy2), _ptr(dpooled), _ptr(ln_w), _ptr(ln_b), _ptr(dm), _ptr(dz_out),
-                          _ptr(dw), _ptr(db), B, C_, L, z.stride(0), z.stride(1), dz_out.stride(0), dz_out.stride(1), _DT[dy2.dtype])
-    _run("vmb_merge_norm_gate_bwd", a, dy2, "merge_bwd", 0, 2)
+    dm = torch.empty((B, C_, L), dtype=dy2.dtype, device=dy2.device) if phase != "params" else None
+    dz = dz_out if phase != "params" else None
+    dw = db = None
+    if phase != "data":
+        dw = torch.zeros(C_, dtype=torch.float32, device=dy2.device) if zeroed is None else zeroed[0]
+        db = torch.zeros(C_, dtype=torch.float32, device=dy2.device) if zeroed is None else zeroed[1]
+    a = _lib.MergeBwdArgs(_ptr(merged), _ptr(stats), _ptr(z), _ptr(dy2), _ptr(dpooled), _ptr(ln_w), _ptr(ln_b), _ptr(dm), _ptr(dz),
+                          _ptr(dw), _ptr(db), B, C_, L, z.stride(0), z.stride(1), dz.stride(0) if dz is not None else 0,
+                          dz.stride(1) if dz is not None else 0, _DT[dy2.dtype])
+    _run("vmb_merge_norm_gate_bwd", a, dy2, "merge_bwd", 0, (1 if dm is not None else 0) + (1 if dw is not None else 0))
+    if phase == "data":
+        return dm
+    if phase == "params":
+        return dw, db
     return dm, dw, db
 
 
-def dwconv3x3_bwd(x, w9, bias, g, c_out, H, W, mode, zeroed=None):
+def dwconv3x3_bwd(x, w9, bias, g, c_out, H, W, mode, zeroed=None, phase="both", dv=None):
     """backward of dwconv3x3 (mode 0 / 1) up to the conv output: -> (dv (B, channels, L), dw9 (channels, 9) fp32, dbias (channels) fp32|None);
-    the input gradient is dwconv3x3(dv, w9.flip(-1), None, channels, H, W, 2)."""
+    the input gradient is dwconv3x3(dv, w9.flip(-1), None, channels, H, W, 2).
+    phase "data": -> dv only;  phase "params" (dv of the "data" call, g unused): -> (dw9, dbias) only."""
     B = x.shape[0]
     ch = c_out * (2 if mode else 1)
-    assert g.stride(2) == 1 and x.stride(2) == 1 and g.dtype == x.dtype
-    dv = torch.empty((B, ch, H * W), dtype=x.dtype, device=x.device)
-    dw = torch.zeros((ch, 9), dtype=torch.float32, device=x.device) if zeroed is None else zeroed[0]
-    dbias = (torch.zeros(ch, dtype=torch.float32, device=x.device) if zeroed is None else zeroed[1]) if bias is not None else None
+    assert x.stride(2) == 1 and phase in ("both", "data", "params")
+    if phase == "params":
+        assert dv is not None and dv.dtype == x.dtype
+        g = None
+    else:
+        assert g.stride(2) == 1 and g.dtype == x.dtype
+        dv = torch.empty((B, ch, H * W), dtype=x.dtype, device=x.device)
+    dw = dbias = None
+    if phase != "data":
+        dw = torch.zeros((ch, 9), dtype=torch.float32, device=x.device) if zeroed is None else zeroed[0]
+        dbias = (torch.zeros(ch, dtype=torch.float32, device=x.device) if zeroed is None else zeroed[1]) if bias is not None else None
     a = _lib.DwconvBwdArgs(_ptr(x), _ptr(w9), _ptr(bias), _ptr(g), _ptr(dv), _ptr(dw), _ptr(dbias), B, c_out, H, W, mode,
-                           x.stride(0), x.stride(1), g.stride(0), g.stride(1), dv.stride(0), dv.stride(1), _DT[x.dtype])
-    _run("vmb_dwconv3x3_bwd", a, x, "dwconv_bwd", 0, 2)
+                           x.stride(0), x.stride(1), g.stride(0) if g is not None else 0, g.stride(1) if g is not None else 0,
+                           dv.stride(0), dv.stride(1), _DT[x.dtype])
+    _run("vmb_dwconv3x3_bwd", a, x, "dwconv_bwd", 0, (1 if g is not None else 0) + (1 if dw is not None else 0))
+    if phase == "data":
+        return dv
+    if phase == "params":
+        return dw, dbias
     return dv, dw, dbias
 
 
