@@ -39,6 +39,34 @@ def test_pixlin_plain(dtype, K, M, P):
     close(out32, ref - bias.view(1, -1, 1), dtype)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("K,M,P,B", [(510, 96, 4096, 4), (512, 96, 1024, 2), (1021, 200, 64, 3), (400, 48, 520, 1), (510, 96, 72, 2)])
+def test_pixlin_kstream_path(dtype, K, M, P, B, monkeypatch):
+    """reduction-heavy plain GEMMs (K > 384: the EFFN / x_proj data gradients of the training path) run the K-streamed kernel:
+    against the fp32 contraction and against the resident-K kernel (VMB_PL_KSTREAM=0), bias / SiLU range / residual, strided views"""
+    from vmambair_b200 import ops
+    torch.manual_seed(K + M)
+    big = torch.randn(B, K + 8, P, device="cuda").to(dtype)
+    x = big[:, 8:]                                         # channel-offset view
+    w = ops.pad_weight((torch.randn(M, K, device="cuda") / K ** 0.5).to(dtype))
+    bias = torch.randn(M, device="cuda")
+    res = torch.randn(B, M, P, device="cuda").to(dtype)
+    ref = torch.einsum("mk,bkp->bmp", w[:, :K].float(), x.float())
+    monkeypatch.setenv("VMB_PIXLIN_TC", "0")
+    outs = {}
+    for ks in ("1", "0"):
+        monkeypatch.setenv("VMB_PL_KSTREAM", ks)
+        o_plain = ops.pixlin(x, w)
+        o_full = ops.pixlin(x, w, bias, residual=res, act=(0, M // 2))
+        outs[ks] = (o_plain, o_full)
+    close(outs["1"][0], ref, dtype)
+    r2 = ref + bias.view(1, -1, 1)
+    r2 = torch.cat([F.silu(r2[:, :M // 2]), r2[:, M // 2:]], 1) + res.float()
+    close(outs["1"][1], r2, dtype, scale=2.0)
+    # same accumulation precision as the resident-K kernel: equal up to the summation order
+    assert (outs["1"][0].float() - outs["0"][0].float()).abs().max() <= 2e-2 * ref.abs().max()
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("ln_mode", [1, 2])
 def test_pixlin_ln_act_residual_gate(dtype, ln_mode):

@@ -575,6 +575,150 @@ static int launch_mma(const PixlinParams& p, int out_dtype, cudaStream_t stream)
                : launch2(pixlin_mma_kernel<in_t, in_t, 64>, p, PT, stream);
 }
 
+
+// ---- K-streamed variant: reduction-heavy plain GEMMs (K > 384, no prologue) ---------------------------------------------------
+// The data gradients W^T dY of the EFFN (2h = 510 -> C = 96) and of the folded x_proj / dt_proj (4(C + 2N) = 512 -> 96) in the
+// training path: the input (K x P) is the big operand, the output small.  The resident-K kernel above re-stages its activation tile
+// per output-channel tile and K chunk without overlap (29.6 us at B = 4, 64x64); here a CTA owns 128 output channels x 64 pixels
+// and walks K in 32-row stages through a 4-deep cp.async ring (W stage [128][32], X stage [32][64]), mma.sync m16n8k16,
+// bias / SiLU range / residual straight from the accumulators.
+constexpr int KS_MT = 128, KS_PT = 64, KS_KC = 32, KS_THREADS = 128;
+constexpr int KS_WP = KS_KC + 8, KS_XP = KS_PT + 8;
+constexpr size_t ks_smem(int stages) { return (size_t)stages * (KS_MT * KS_WP + KS_KC * KS_XP) * 2; }
+
+template <typename in_t, int KS_ST>
+__global__ void __launch_bounds__(KS_THREADS) pixlin_kstream_kernel(const PixlinParams p) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    in_t* sW = reinterpret_cast<in_t*>(smem_raw);          // [ST][128][WP]
+    in_t* sX = sW + (size_t)KS_ST * KS_MT * KS_WP;         // [ST][KC][XP]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 1, wn = warp & 1;               // 2 x 2 warps: 64 output channels x 32 pixels each
+    const int b = blockIdx.z, p0 = blockIdx.x * KS_PT, m0 = blockIdx.y * KS_MT;
+    const int kpad16 = (p.K + 15) / 16 * 16;
+    const int kw = p.w_ld < kpad16 ? (int)p.w_ld : kpad16;  // weight columns that exist (zero-padded beyond K)
+    const int nk = (p.K + KS_KC - 1) / KS_KC;
+    const in_t* __restrict__ xb = reinterpret_cast<const in_t*>(p.x) + (int64_t)b * p.x_bs;
+    const in_t* __restrict__ wg = reinterpret_cast<const in_t*>(p.w);
+
+    auto stage = [&](int kt) {
+        const int buf = kt % KS_ST, k0 = kt * KS_KC;
+        in_t* w_s = sW + (size_t)buf * KS_MT * KS_WP;
+        in_t* x_s = sX + (size_t)buf * KS_KC * KS_XP;
+#pragma unroll
+        for (int it = tid; it < KS_MT * (KS_KC / 8); it += KS_THREADS) {
+            const int row = it / (KS_KC / 8), c = (it % (KS_KC / 8)) * 8;
+            const int m = m0 + row, k = k0 + c;
+            const bool ok = m < p.M && k + 8 <= kw;
+            cp_async16_pl(w_s + row * KS_WP + c, ok ? (const void*)(wg + (int64_t)m * p.w_ld + k) : (const void*)wg, ok ? 16 : 0);
+        }
+#pragma unroll
+        for (int it = tid; it < KS_KC * (KS_PT / 8); it += KS_THREADS) {
+            const int row = it / (KS_PT / 8), c = (it % (KS_PT / 8)) * 8;
+            const int k = k0 + row, px = p0 + c;
+            const bool ok = k < p.K && px < p.P;  // P % 8 == 0 (vec_ok): whole vectors
+            cp_async16_pl(x_s + row * KS_XP + c, ok ? (const void*)(xb + (int64_t)k * p.x_cs + px) : (const void*)xb, ok ? 16 : 0);
+        }
+    };
+
+    float acc[4][4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < KS_ST - 1; ++s) {
+        if (s < nk) stage(s);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(KS_ST - 2) : "memory");
+        __syncthreads();  // stage kt landed for everyone; everyone is done with stage kt-1 (whose buffer is refilled next)
+        if (kt + KS_ST - 1 < nk) stage(kt + KS_ST - 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const in_t* w_s = sW + (size_t)(kt % KS_ST) * KS_MT * KS_WP;
+        const in_t* x_s = sX + (size_t)(kt % KS_ST) * KS_KC * KS_XP;
+#pragma unroll
+        for (int kk = 0; kk < KS_KC; kk += 16) {
+            uint32_t af[4][4], bf[4][2];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(w_s + (wm * 64 + mi * 16 + (lane & 15)) * KS_WP + kk + ((lane >> 4) << 3)));
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(af[mi][0]), "=r"(af[mi][1]), "=r"(af[mi][2]), "=r"(af[mi][3]) : "r"(sa));
+            }
+#pragma unroll
+            for (int nj = 0; nj < 4; nj += 2) {
+                const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(x_s + (kk + (lane & 15)) * KS_XP + wn * 32 + nj * 8 + ((lane >> 4) << 3)));
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(bf[nj][0]), "=r"(bf[nj][1]), "=r"(bf[nj + 1][0]), "=r"(bf[nj + 1][1]) : "r"(sa));
+            }
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int nj = 0; nj < 4; ++nj) MmaType<in_t>::mma(acc[mi][nj], af[mi], bf[nj]);
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // epilogue straight from the accumulators: each thread owns 2 adjacent pixels of its (row, n8) fragments
+    const in_t* __restrict__ res = p.residual ? reinterpret_cast<const in_t*>(p.residual) + (int64_t)b * p.r_bs : nullptr;
+    in_t* __restrict__ ob = reinterpret_cast<in_t*>(p.out) + (int64_t)b * p.o_bs;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int mg = m0 + wm * 64 + mi * 16 + hf * 8 + (lane >> 2);
+            if (mg >= p.M) continue;
+            const float bs = p.bias ? p.bias[mg] : 0.f;
+            const bool act = mg >= p.act_from && mg < p.act_to;
+#pragma unroll
+            for (int nj = 0; nj < 4; ++nj) {
+                const int pg = p0 + wn * 32 + nj * 8 + 2 * (lane & 3);
+                if (pg >= p.P) continue;
+                float v0 = acc[mi][nj][hf * 2] + bs, v1 = acc[mi][nj][hf * 2 + 1] + bs;
+                if (act) {
+                    v0 = silu_f(v0);
+                    v1 = silu_f(v1);
+                }
+                if (res) {
+                    const float2 r2 = unpack2<in_t>(*reinterpret_cast<const uint32_t*>(res + (int64_t)mg * p.r_cs + pg));
+                    v0 += r2.x;
+                    v1 += r2.y;
+                }
+                *reinterpret_cast<uint32_t*>(ob + (int64_t)mg * p.o_cs + pg) = pack2<in_t>(v0, v1);
+            }
+        }
+}
+
+template <typename in_t, int ST>
+static int launch_kstream2(const PixlinParams& p, cudaStream_t stream) {
+    auto kern = pixlin_kstream_kernel<in_t, ST>;
+    VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks_smem(ST)));
+    dim3 grid((p.P + KS_PT - 1) / KS_PT, (p.M + KS_MT - 1) / KS_MT, p.B);
+    VMB_CHECK(grid.y <= 65535, "pixlin: too many output channels");
+    VMB_CUDA(launch_pdl(kern, grid, dim3(KS_THREADS), ks_smem(ST), stream, p));
+    VMB_CUDA(cudaGetLastError());
+    return VMB_OK;
+}
+template <typename in_t>
+static int launch_kstream(const PixlinParams& p, cudaStream_t stream) {
+    int st = 6;  // ring depth: bytes in flight per SM
+    if (const char* e = getenv("VMB_KS_ST")) st = atoi(e);
+    return st == 4 ? launch_kstream2<in_t, 4>(p, stream) : launch_kstream2<in_t, 6>(p, stream);
+}
+
+static bool kstream_applicable(const PixlinParams& p, int dtype, int out_dtype) {
+    if (const char* e = getenv("VMB_PL_KSTREAM")) {
+        if (atoi(e) == 0) return false;
+    }
+    return (dtype == VMB_BF16 || dtype == VMB_F16) && out_dtype == dtype && p.ln_mode == 0 && p.gate_mode == 0 && p.vec_ok && p.w_vec &&
+           p.K > PL2_KC && p.M <= 2 * KS_MT;
+}
+
 template <typename K>
 static int launch(K kern, const PixlinParams& p, size_t smem, cudaStream_t stream) {
     if (smem > 48 * 1024) VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -593,6 +737,8 @@ int pixlin_launch(const PixlinParams& p, int dtype, int out_dtype, cudaStream_t 
               dtype == VMB_F32 ? PL_KC / 2 : PL2_KC);
     VMB_CHECK(p.gate_mode == 0 || p.K <= (dtype == VMB_F32 ? PL_KC / 2 : PL2_KC), "pixlin: gate prologue needs resident K");
     if (pixlin_tc_applicable(p, dtype, out_dtype)) return pixlin_tc_launch(p, dtype, stream);  // tcgen05 / TMEM path
+    if (kstream_applicable(p, dtype, out_dtype))
+        return dtype == VMB_BF16 ? launch_kstream<__nv_bfloat16>(p, stream) : launch_kstream<__half>(p, stream);
     const size_t smem = pixlin_smem(p.K, dtype == VMB_F32 ? 4 : 2);
     if (dtype == VMB_F32) {
         VMB_CHECK(out_dtype == VMB_F32, "pixlin: fp32 input needs fp32 output");
