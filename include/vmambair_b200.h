@@ -159,7 +159,9 @@ int vmb_pixel_shuffle2_nhwc(const vmb_pixel_shuffle_args* a, void* stream);
 
 /* inverse orders + 4-way fp32 sum (:427-430 / CrossMerge) + out_norm (:433) + gate y*SiLU(z) (:493) +
  * per-(b,c) sums of the result for AdaptiveAvgPool2d (:441; `pooled` fp32 (B,C), fully written).
- * workspace: vmb_merge_workspace_bytes() bytes of device scratch (fp32 merged values + per-pixel statistics). */
+ * workspace: vmb_merge_workspace_bytes() bytes of device scratch (fp32 merged values + per-pixel statistics + tile sums).
+ * 16-bit I/O with H, W multiples of 16 and C <= 96 runs ONE kernel (all channels of a 16x16 pixel tile per CTA, no atomics on the
+ * statistics); other shapes a channel-split sum kernel + a normalisation kernel. */
 typedef struct {
     const void* ys; const void* z; const float* ln_w; const float* ln_b; void* y2; float* pooled;
     int batch, C, H, W;
@@ -170,6 +172,8 @@ typedef struct {
                            ys[1],ys[3] in transposed (W,H) pixel order (outputs of vmb_selective_scan_fwd_grouped) */
     int z_preact;       /* 0: z already holds SiLU(z) (inference: the in_conv epilogue applied it); 1: z is the pre-activation
                            and SiLU is applied here (training: the backward needs the pre-activation) */
+    int save_ws;        /* 1: the workspace keeps the fp32 merged values (B,C,L) followed by the per-pixel (sum, sum of squares)
+                           over C (B,L,2) for vmb_merge_norm_gate_bwd; 0: its content is unspecified afterwards */
 } vmb_merge_args;
 int vmb_merge_norm_gate(const vmb_merge_args* a, void* stream);
 int64_t vmb_merge_workspace_bytes(int batch, int C, int H, int W);

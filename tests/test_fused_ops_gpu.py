@@ -179,6 +179,47 @@ def test_merge_norm_gate(dtype, C, H, W):
     torch.testing.assert_close(pooled.cpu(), y2.float().sum(-1).cpu(), rtol=2e-3, atol=2e-2)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("C,H,W,B", [(96, 64, 64, 3), (48, 32, 16, 2), (96, 16, 48, 1), (50, 16, 16, 2), (130, 32, 32, 1)])
+@pytest.mark.parametrize("inplace", [False, True])
+def test_merge_single_kernel_path(dtype, C, H, W, B, inplace, monkeypatch):
+    """H, W multiples of 16 and C <= 146: ONE kernel (16 x 16 pixel tiles, all channels per CTA, cp.async ring over the channels).
+    Against the fp32 composition, against the two-kernel path (VMB_MERGE_FUSED=0), both direction layouts, SiLU inside or outside,
+    and the workspace handed to the backward (merged fp32 values + per-pixel sum / sum of squares)."""
+    from vmambair_b200 import ops
+    torch.manual_seed(C + H)
+    L = H * W
+    ys = torch.randn(B, 4, C, L, device="cuda").to(dtype)
+    zbig = torch.randn(B, 2 * C, L, device="cuda").to(dtype)
+    z = zbig[:, C:]
+    lw, lb = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda") * 0.1
+    f = ys.float()
+    T = lambda t: t.view(B, C, W, H).transpose(2, 3).reshape(B, C, L)
+    if inplace:
+        y = ((f[:, 0] + f[:, 2]) + T(f[:, 1])) + T(f[:, 3])
+    else:
+        y = ((f[:, 0] + f[:, 2].flip(-1)) + T(f[:, 1])) + T(f[:, 3].flip(-1))
+    yn = ln_ref(y, lw, lb).to(dtype).float()
+    out = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("VMB_MERGE_FUSED", fused)
+        y2a, pa = ops.merge_norm_gate(ys, z, lw, lb, C, H, W, in_place_order=inplace)
+        y2b, pb, ws = ops.merge_norm_gate(ys, z, lw, lb, C, H, W, in_place_order=inplace, z_preact=True, return_ws=True)
+        out[fused] = (y2a, pa, y2b, pb, ws.view(torch.float32)[:B * C * L + 2 * B * L].clone())
+    y2a, pa, y2b, pb, ws = out["1"]
+    close(y2a, yn * z.float(), dtype, scale=2.0)
+    close(y2b, yn * F.silu(z.float()), dtype, scale=2.0)
+    torch.testing.assert_close(pa, y2a.float().sum(-1), rtol=2e-3, atol=2e-2)
+    torch.testing.assert_close(pb, y2b.float().sum(-1), rtol=2e-3, atol=2e-2)
+    # the merged fp32 values are bit-identical to the two-kernel path (same summation order); the statistics differ by their own
+    # summation order over the channels only
+    assert torch.equal(ws[:B * C * L], out["0"][4][:B * C * L])
+    torch.testing.assert_close(ws[:B * C * L].view(B, C, L), y, rtol=0, atol=0)
+    torch.testing.assert_close(ws[B * C * L:], out["0"][4][B * C * L:], rtol=1e-5, atol=1e-4)
+    # outputs of the two paths: equal except where the last bit of the statistics moved a rounding boundary
+    assert (y2a.float() - out["0"][0].float()).abs().max() <= 2e-2 * y2a.float().abs().max()
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("C,H,W", [(48, 16, 24), (96, 64, 64), (32, 8, 8), (16, 40, 24)])
 def test_grouped_direction_aware_scan_equals_gathered_scan(dtype, C, H, W):

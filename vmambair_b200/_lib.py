@@ -72,7 +72,7 @@ class MergeArgs(C.Structure):
         ("ys", vp), ("z", vp), ("ln_w", vp), ("ln_b", vp), ("y2", vp), ("pooled", vp),
         ("batch", C.c_int), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int),
         ("z_bs", i64), ("z_cs", i64), ("dtype", C.c_int), ("workspace", vp), ("in_place_order", C.c_int),
-        ("z_preact", C.c_int),
+        ("z_preact", C.c_int), ("save_ws", C.c_int),
     ]
 
 

@@ -150,14 +150,16 @@ extern "C" int vmb_cross_scan(const vmb_cross_scan_args* a, void* stream) {
 }
 
 extern "C" int64_t vmb_merge_workspace_bytes(int batch, int C, int H, int W) {
-    return 4 * ((int64_t)batch * C * H * W + 2 * (int64_t)batch * H * W);
+    // fp32 merged values + per-pixel (sum, sum of squares) + per-tile channel sums + per-image tile counters of the single-kernel path
+    const int64_t tiles = (int64_t)((H + 15) / 16) * ((W + 15) / 16);
+    return 4 * ((int64_t)batch * C * H * W + 2 * (int64_t)batch * H * W + (int64_t)batch * tiles * C + batch) + 16;
 }
 
 extern "C" int vmb_merge_norm_gate(const vmb_merge_args* a, void* stream) {
     VMB_CHECK(a && a->ys && a->z && a->ln_w && a->ln_b && a->y2 && a->pooled, "merge: null pointer");
     VMB_CHECK(dt_ok(a->dtype), "merge: bad dtype");
     VMB_CHECK(a->batch > 0 && a->batch <= 65535, "merge: bad batch");
-    MergeParams p{a->ys, a->z, a->ln_w, a->ln_b, a->y2, a->pooled, a->batch, a->C, a->H, a->W, a->z_bs, a->z_cs, a->in_place_order, a->workspace, a->z_preact};
+    MergeParams p{a->ys, a->z, a->ln_w, a->ln_b, a->y2, a->pooled, a->batch, a->C, a->H, a->W, a->z_bs, a->z_cs, a->in_place_order, a->workspace, a->z_preact, a->save_ws};
     VMB_CHECK(a->workspace && aligned16(a->workspace), "merge: 16 B-aligned workspace of vmb_merge_workspace_bytes() required");
     return merge_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
 }

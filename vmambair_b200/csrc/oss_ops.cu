@@ -563,11 +563,231 @@ __global__ void __launch_bounds__(256) norm_gate_pool_kernel(const MergeParams p
     }
 }
 
+
+// ---- single-kernel variant (round 2): 16-bit I/O, H % 16 == 0, W % 16 == 0, C <= 96 ------------------------------------------------
+// The judgement above ("too few CTAs") was about a CTA that also walks its channels serially with exposed load latency.  Here a CTA
+// of 512 threads owns a 16 x 16 pixel tile and ALL channels, and the four direction tiles of 4 channels at a time arrive through a
+// 4-deep cp.async ring in their MEMORY order (32 B row segments of the (H,W)-ordered directions 0 / 2, 32 B column segments of the
+// (W,H)-ordered directions 1 / 3, mirrored segments for the reversed scan orders), so that phase 1 (thread = pixel: the reference's
+// ((y0 + flip y2) + T y1) + T flip y3, fp32, into the smem tile [C][256], per-pixel sum / sum of squares in registers -- no
+// atomics, no memset) never waits for a load.  Phase 2 (thread = 8-pixel vector x channel slice): LayerNorm with the per-pixel
+// statistics, gate, 16 B stores, per-channel tile sums; the last CTA of an image (counter in the workspace) adds the tile sums in a
+// fixed order into `pooled` -- deterministic, unlike a float atomicAdd.
+constexpr int MF_CG = 4, MF_ST = 4, MF_PITCH = 24;
+constexpr int MF_MAXPW = 6;                                           // channels per warp in phase 2 (16 warps: C <= 96)                    // channels per stage, ring depth, tile row pitch (elements)
+constexpr int MF_STAGE = MF_CG * 4 * 16 * MF_PITCH;                   // elements of one ring stage
+__host__ __device__ constexpr size_t merge_fused_smem(int C) {
+    return sizeof(float) * ((size_t)C * 256 + 512) + 2 * (size_t)MF_ST * MF_STAGE + 16;
+}
+
+template <typename in_t>
+__global__ void __launch_bounds__(512) merge_fused_kernel(const MergeParams p, float* __restrict__ msum, float* __restrict__ stats,
+                                                          float* __restrict__ parts, unsigned* __restrict__ counters, const int save_ws) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ __align__(16) unsigned char mf_raw[];
+    const int C = p.C, H = p.H, W = p.W, L = H * W;
+    float* sSum = reinterpret_cast<float*>(mf_raw);                    // [C][256]
+    float* sMu = sSum + (size_t)C * 256;                               // [256]
+    float* sRs = sMu + 256;                                            // [256]
+    in_t* sRing = reinterpret_cast<in_t*>(sRs + 256);                  // [MF_ST][4 ch][4 dir][16][MF_PITCH]
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    const int tiles_w = W / 16, ntiles = (H / 16) * tiles_w;
+    const int tile = blockIdx.x, b = blockIdx.y;
+    const int h0 = (tile / tiles_w) * 16, w0 = (tile % tiles_w) * 16;
+    const int64_t CL = (int64_t)C * L;
+    const in_t* __restrict__ ys = reinterpret_cast<const in_t*>(p.ys) + (int64_t)b * 4 * CL;
+    const int ngroups = (C + MF_CG - 1) / MF_CG;
+    const bool inplace = p.in_place_order != 0;
+
+    // 512 16-byte chunks per stage, one per thread: chunk -> (direction k, channel cl of the group, tile row r, half row); everything
+    // but the channel group is loop-invariant, so the source pointer advances by 4 channels per stage and nothing else is recomputed
+    const in_t* csrc;
+    uint32_t cdst;
+    int ccl;
+    {
+        const int k = tid >> 7, cl = (tid >> 5) & 3, r = (tid >> 1) & 15, half = tid & 1;
+        int64_t idx;
+        if ((k & 1) == 0) idx = (int64_t)(h0 + r) * W + w0;        // directions 0 / 2: row r of the tile, 16 consecutive w
+        else idx = (int64_t)(w0 + r) * H + h0;                     // directions 1 / 3: column r of the tile, 16 consecutive h
+        if (k >= 2 && !inplace) idx = (int64_t)L - 16 - idx;        // reversed scan order: the mirrored 16-element segment
+        csrc = ys + (int64_t)k * CL + (int64_t)cl * L + idx + 8 * half;
+        cdst = static_cast<uint32_t>(__cvta_generic_to_shared(sRing + ((cl * 4 + k) * 16 + r) * MF_PITCH + 8 * half));
+        ccl = cl;
+    }
+    const int64_t gstep = (int64_t)MF_CG * L;
+    auto issue = [&](int g) {
+        const uint32_t soff = (uint32_t)((g % MF_ST) * MF_STAGE * (int)sizeof(in_t));
+        const bool ok = g * MF_CG + ccl < C;
+        const in_t* src = ok ? csrc + (int64_t)g * gstep : ys;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(cdst + soff), "l"(src), "r"(ok ? 16 : 0) : "memory");
+    };
+#pragma unroll
+    for (int g = 0; g < MF_ST - 1; ++g) {
+        if (g < ngroups) issue(g);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // the gate operand of phase 2 (this lane's 8-pixel vector of every channel of its warp's slice) is fetched now: it lands while
+    // phase 1 runs
+    const int lane = tid & 31, warp = tid >> 5;
+    const int vh = lane >> 1, vw = (lane & 1) * 8;
+    const int l0 = (h0 + vh) * W + w0 + vw;
+    uint4 zr[MF_MAXPW];
+    {
+        const in_t* __restrict__ zb = reinterpret_cast<const in_t*>(p.z) + (int64_t)b * p.z_bs + l0;
+#pragma unroll
+        for (int j = 0; j < MF_MAXPW; ++j) {
+            const int c = warp + 16 * j;
+            zr[j] = c < C ? ldg128(zb + (int64_t)c * p.z_cs) : make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    // phase 1: thread = (channel half of the group, pixel (th, tw))
+    const int hsel = tid >> 8, pix = tid & 255;
+    const int th = pix >> 4, tw = pix & 15;
+    const int o2 = inplace ? tw : 15 - tw;   // position of this pixel inside the (possibly mirrored) row segment of direction 2
+    const int o3 = inplace ? th : 15 - th;   // ... inside the column segment of direction 3
+    const int r0 = (0 * 16 + th) * MF_PITCH + tw, r1 = (1 * 16 + tw) * MF_PITCH + th;
+    const int r2 = (2 * 16 + th) * MF_PITCH + o2, r3 = (3 * 16 + tw) * MF_PITCH + o3;
+    float s1 = 0.f, s2 = 0.f;
+    float* sumcol = sSum + pix;
+#pragma unroll 1
+    for (int g = 0; g < ngroups; ++g) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(MF_ST - 2) : "memory");
+        __syncthreads();  // stage g landed for every thread; stage g-1 is free again
+        if (g + MF_ST - 1 < ngroups) issue(g + MF_ST - 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const in_t* st = sRing + (size_t)(g % MF_ST) * MF_STAGE;
+#pragma unroll
+        for (int j = 0; j < MF_CG / 2; ++j) {
+            const int cl = 2 * hsel + j;
+            const int c = g * MF_CG + cl;
+            if (c < C) {
+                const in_t* t = st + cl * 4 * 16 * MF_PITCH;
+                const float y0 = to_f32<in_t>(t[r0]);
+                const float y1 = to_f32<in_t>(t[r1]);
+                const float y2 = to_f32<in_t>(t[r2]);
+                const float y3 = to_f32<in_t>(t[r3]);
+                const float v = ((y0 + y2) + y1) + y3;
+                sumcol[c * 256] = v;
+                s1 += v;
+                s2 = fmaf(v, v, s2);
+            }
+        }
+    }
+    // per-pixel statistics: the two channel halves meet in smem (sMu / sRs double as the exchange buffer)
+    if (hsel == 1) {
+        sMu[pix] = s1;
+        sRs[pix] = s2;
+    }
+    __syncthreads();
+    if (hsel == 0) {
+        s1 += sMu[pix];
+        s2 += sRs[pix];
+        const float invC = 1.f / C;
+        const float mu = s1 * invC;
+        sMu[pix] = mu;
+        sRs[pix] = rsqrtf(fmaxf(s2 * invC - mu * mu, 0.f) + 1e-5f);
+        if (save_ws) {
+            const int l = (h0 + th) * W + w0 + tw;
+            *reinterpret_cast<float2*>(stats + ((int64_t)b * L + l) * 2) = make_float2(s1, s2);
+        }
+    }
+    __syncthreads();
+    // phase 2: lane = 8-pixel vector of the tile (row lane/2, half lane%2), warp = channel slice (z vectors prefetched above)
+    float mu8[8], rs8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        mu8[i] = sMu[vh * 16 + vw + i];
+        rs8[i] = sRs[vh * 16 + vw + i];
+    }
+    in_t* __restrict__ ob = reinterpret_cast<in_t*>(p.y2) + (int64_t)b * CL;
+    const bool zact = p.z_preact != 0;
+#pragma unroll
+    for (int j = 0; j < MF_MAXPW; ++j) {
+        const int c = warp + 16 * j;
+        if (c < C) {
+            float zv[8], m8[8], o8[8];
+            unpack8<in_t>(zr[j], zv);
+            *reinterpret_cast<float4*>(m8) = *reinterpret_cast<const float4*>(sSum + c * 256 + vh * 16 + vw);
+            *reinterpret_cast<float4*>(m8 + 4) = *reinterpret_cast<const float4*>(sSum + c * 256 + vh * 16 + vw + 4);
+            const float lw = p.ln_w[c], lb = p.ln_b[c];
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float nrm = (m8[i] - mu8[i]) * rs8[i] * lw + lb;
+                const float n_r = to_f32<in_t>(from_f32<in_t>(nrm));  // the reference rounds y1 to the activation dtype before the gate
+                const in_t y = from_f32<in_t>(n_r * (zact ? silu2(zv[i]) : zv[i]));
+                o8[i] = to_f32<in_t>(y);
+                acc += o8[i];
+            }
+            store_vec<in_t>(ob + (int64_t)c * L + l0, o8, 8, true);
+            if (save_ws) {
+                float* mrow = msum + ((int64_t)b * C + c) * L + l0;
+                *reinterpret_cast<float4*>(mrow) = *reinterpret_cast<const float4*>(m8);
+                *reinterpret_cast<float4*>(mrow + 4) = *reinterpret_cast<const float4*>(m8 + 4);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (lane == 0) parts[((int64_t)b * ntiles + tile) * C + c] = acc;
+        }
+    }
+    // the last tile of the image adds the tile sums, in tile order
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(counters + b, 1u) == (unsigned)(ntiles - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        for (int c = tid; c < C; c += 512) {
+            float t = 0.f;
+            for (int i = 0; i < ntiles; ++i) t += __ldcg(parts + ((int64_t)b * ntiles + i) * C + c);
+            p.pooled[(int64_t)b * C + c] = t;
+        }
+        if (tid == 0) counters[b] = 0;  // ready for the next launch on this workspace
+    }
+}
+
+// the workspace regions of the fused kernel sit behind the fp32 merged values and the statistics
+static bool merge_fused_applicable(const MergeParams& p, int dtype) {
+    int mode = 2;  // VMB_MERGE_FUSED: 0 never, 1 whenever legal (tests), default: where it was measured faster
+    if (const char* e = getenv("VMB_MERGE_FUSED")) mode = atoi(e);
+    if (mode == 0) return false;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool legal = (dtype == VMB_BF16 || dtype == VMB_F16) && p.H % 16 == 0 && p.W % 16 == 0 && p.C <= 16 * MF_MAXPW &&
+                       merge_fused_smem(p.C) <= 200 * 1024 && al16(p.ys) && al16(p.z) && al16(p.y2) && p.z_bs % 8 == 0 && p.z_cs % 8 == 0;
+    if (!legal || mode == 1) return legal;
+    // tools/merge_bench.py (bf16, sustained): 2 x 96 x 128x128: 24.6 vs 47.7 us (the normalisation kernel of the two-kernel path walks
+    // all pixels of a channel in one CTA); 8 x 96 x 64x64: 24.6 vs 24.9, 8 x 96 x 32x32: 22 vs 8.4 -- a CTA of the single kernel
+    // needs ~20 us for its 24 channel groups at any size, so it pays from 128 x 128 pixels per image up
+    return (long)p.H * p.W >= 16384;
+}
+
 int merge_launch(const MergeParams& p, int dtype, cudaStream_t stream) {
     VMB_CHECK(p.ws != nullptr, "merge: workspace missing");
     const int L = p.H * p.W;
     float* msum = reinterpret_cast<float*>(p.ws);
     float* stats = msum + (size_t)p.B * p.C * L;
+    if (merge_fused_applicable(p, dtype)) {
+        const int ntiles = (p.H / 16) * (p.W / 16);
+        float* parts = stats + 2 * (size_t)p.B * L;
+        unsigned* counters = reinterpret_cast<unsigned*>(parts + (size_t)p.B * ntiles * p.C);
+        const size_t smem = merge_fused_smem(p.C);
+        VMB_CHECK(p.B <= 65535, "merge: batch > 65535");
+        VMB_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned) * p.B, stream));  // (the kernel also leaves them at zero)
+        dim3 grid(ntiles, p.B);
+        if (dtype == VMB_BF16) {
+            auto k = merge_fused_kernel<__nv_bfloat16>;
+            VMB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k<<<grid, 512, smem, stream>>>(p, msum, stats, parts, counters, p.save_ws);
+        } else {
+            auto k = merge_fused_kernel<__half>;
+            VMB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k<<<grid, 512, smem, stream>>>(p, msum, stats, parts, counters, p.save_ws);
+        }
+        VMB_CUDA(cudaGetLastError());
+        return VMB_OK;
+    }
     VMB_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)p.B * L, stream));
     dim3 gridA(((p.H + 15) / 16) * ((p.W + 15) / 16), (p.C + MG_CH - 1) / MG_CH, p.B);
     dim3 gridB(p.C, p.B);

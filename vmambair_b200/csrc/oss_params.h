@@ -31,6 +31,7 @@ struct MergeParams {
     int in_place_order;
     void* ws;  // fp32 scratch: B*C*L merged values + 2*B*L per-pixel statistics
     int z_preact;
+    int save_ws;  // keep the merged values / statistics in ws for the backward (the two-kernel path always does)
 };
 struct TransposeParams {
     const void* x; void* out;

@@ -267,7 +267,7 @@ def merge_norm_gate(ys, z, ln_w, ln_b, C_, H, W, in_place_order=False, z_preact=
     pooled = torch.empty((B, C_), dtype=torch.float32, device=ys.device)
     ws = torch.empty(_lib.lib().vmb_merge_workspace_bytes(B, C_, H, W), dtype=torch.uint8, device=ys.device)
     a = _lib.MergeArgs(_ptr(ys), _ptr(z), _ptr(ln_w), _ptr(ln_b), _ptr(y2), _ptr(pooled), B, C_, H, W,
-                       z.stride(0), z.stride(1), _DT[ys.dtype], _ptr(ws), int(in_place_order), int(z_preact))
+                       z.stride(0), z.stride(1), _DT[ys.dtype], _ptr(ws), int(in_place_order), int(z_preact), int(return_ws))
     _run("vmb_merge_norm_gate", a, ys, "merge", 0, 2)
     return (y2, pooled, ws) if return_ws else (y2, pooled)
 
