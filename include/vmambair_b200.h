@@ -157,6 +157,35 @@ int vmb_transpose_hw(const vmb_transpose_args* a, void* stream);
 typedef struct { const void* x; void* out; int batch, H, W, C; int dtype; } vmb_pixel_shuffle_args;
 int vmb_pixel_shuffle2_nhwc(const vmb_pixel_shuffle_args* a, void* stream);
 
+/* Dense 3x3 convolution, stride 1, zero padding 1 -- the non-OSS convolutions of the U-Net:
+ * OverlapPatchEmbed.proj (SRGAN/VmambaIR/archs/MambaSISR6_arch.py:520-528), Downsample.body = Conv2d + PixelUnshuffle(2)
+ * (:533-541), Upsample.body = Conv2d + PixelShuffle(2) (:544-553), the SR tail's last conv + the nearest-neighbour up-sampled
+ * input (:607,640; Upsampler in archs/common.py:45-60), Mamber32.output + inp_img (Deraining mamber32_arch.py forward).
+ * What the reference runs as separate passes behind the conv is index arithmetic of the store:
+ *   mode VMB_CONV_PLAIN        out[b, m, y, x]                                   (out may be a channel slice of a wider tensor:
+ *                                                                                 the decoder's torch.cat([up, skip], 1) never runs)
+ *        VMB_CONV_UNSHUFFLE2   out[b, 4m + 2(y%2) + x%2, y/2, x/2]               nn.PixelUnshuffle(2); H, W even
+ *        VMB_CONV_SHUFFLE2     out[b, m/4, 2y + (m/2)%2, 2x + m%2]               nn.PixelShuffle(2); Cout % 4 == 0
+ *        VMB_CONV_ADD_NEAREST  out[b, m, y, x] = conv + add[b, m, y/s, x/s]      F.interpolate(add, scale_factor=s, 'nearest'), s >= 1
+ * x: NCHW view (x_bs, x_cs element strides; planes dense) or, in_nhwc = 1, dense NHWC (B,H,W,Cin) with Cin % 8 == 0.
+ * out: NCHW planes dense with (o_bs, o_cs) strides; its spatial size is (H/2, W/2), (2H, 2W) or (H, W) by mode.
+ * w: the Conv2d weight (Cout, Cin, 3, 3) re-packed by the caller as [tap = 3*ky + kx][Mpad][Kpad] in the I/O dtype, zero padded,
+ *    Mpad = Cout rounded up to 64, Kpad = Cin rounded up to 16 (static parameters: the kernel may read them before the preceding
+ *    kernel of the stream has finished).  bias: fp32 (Cout) or NULL.  16-bit I/O: tensor-core implicit GEMM, fp32 accumulation;
+ *    fp32 I/O: FFMA. */
+#define VMB_CONV_PLAIN 0
+#define VMB_CONV_UNSHUFFLE2 1
+#define VMB_CONV_SHUFFLE2 2
+#define VMB_CONV_ADD_NEAREST 3
+typedef struct {
+    const void* x; const void* w; const float* bias; void* out; const void* add;
+    int batch, Cin, Cout, H, W;
+    int in_nhwc, mode, add_scale;
+    int64_t x_bs, x_cs, o_bs, o_cs, add_bs, add_cs;
+    int dtype;
+} vmb_conv3x3_args;
+int vmb_conv3x3(const vmb_conv3x3_args* a, void* stream);
+
 /* inverse orders + 4-way fp32 sum (:427-430 / CrossMerge) + out_norm (:433) + gate y*SiLU(z) (:493) +
  * per-(b,c) sums of the result for AdaptiveAvgPool2d (:441; `pooled` fp32 (B,C), fully written).
  * workspace: vmb_merge_workspace_bytes() bytes of device scratch (fp32 merged values + per-pixel statistics + tile sums).

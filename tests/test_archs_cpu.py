@@ -113,3 +113,17 @@ def test_product_path_has_no_cpu_fallback():
     with pytest.raises(RuntimeError):
         t = torch.zeros(1, 4, 8)
         ops.selective_scan_fwd(t, t, torch.zeros(4, 16), torch.zeros(1, 1, 16, 8), torch.zeros(1, 1, 16, 8))
+
+
+def test_pack_conv3x3_weight_layout():
+    """[tap = 3 ky + kx][Cout -> x64][Cin -> x16], zero padded: a conv evaluated tap by tap from the packed tensor = F.conv2d"""
+    import torch.nn.functional as F
+    from vmambair_b200 import ops
+    torch.manual_seed(0)
+    w = torch.randn(5, 7, 3, 3)
+    x = torch.randn(2, 7, 6, 9)
+    wp = ops.pack_conv3x3_weight(w, torch.float32)
+    assert wp.shape == (9, 64, 16) and float(wp[:, 5:].abs().max()) == 0 and float(wp[:, :, 7:].abs().max()) == 0
+    xp = F.pad(x, (1, 1, 1, 1))
+    y = sum(torch.einsum("mk,bkhw->bmhw", wp[3 * ky + kx, :5, :7], xp[:, :, ky:ky + 6, kx:kx + 9]) for ky in range(3) for kx in range(3))
+    torch.testing.assert_close(y, F.conv2d(x, w, padding=1), rtol=1e-5, atol=1e-5)

@@ -84,6 +84,16 @@ class PixelShuffleArgs(C.Structure):
     _fields_ = [("x", vp), ("out", vp), ("batch", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("dtype", C.c_int)]
 
 
+class Conv3x3Args(C.Structure):
+    _fields_ = [
+        ("x", vp), ("w", vp), ("bias", vp), ("out", vp), ("add", vp),
+        ("batch", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("in_nhwc", C.c_int), ("mode", C.c_int), ("add_scale", C.c_int),
+        ("x_bs", i64), ("x_cs", i64), ("o_bs", i64), ("o_cs", i64), ("add_bs", i64), ("add_cs", i64),
+        ("dtype", C.c_int),
+    ]
+
+
 class ScanGroupedArgs(C.Structure):
     _fields_ = [
         ("u", vp * 4), ("delta", vp * 4), ("Bm", vp * 4), ("Cm", vp * 4), ("out", vp * 4), ("rev", C.c_int * 4),
@@ -178,6 +188,7 @@ SYMBOLS = {
     "vmb_merge_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "vmb_transpose_hw": (C.c_int, [C.POINTER(TransposeArgs), vp]),
     "vmb_pixel_shuffle2_nhwc": (C.c_int, [C.POINTER(PixelShuffleArgs), vp]),
+    "vmb_conv3x3": (C.c_int, [C.POINTER(Conv3x3Args), vp]),
     "vmb_selective_scan_fwd_grouped": (C.c_int, [C.POINTER(ScanGroupedArgs), vp]),
     "vmb_channel_branch": (C.c_int, [C.POINTER(ChannelArgs), vp]),
     "vmb_layernorm_fwd": (C.c_int, [C.POINTER(LnFwdArgs), vp]),

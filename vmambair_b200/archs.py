@@ -279,16 +279,21 @@ class MamberBlock(nn.Module):
         x = x + self.attn.forward_compose(self.norm1(x))
         return x + self.ffn(self.norm2(x))
 
-    def forward(self, x):
+    def forward(self, x, out=None):
+        """out (inference only, vmambair_b200.unet): optional destination view (a channel slice of a concatenation buffer)"""
         if x.is_cuda:
             from . import fused
             if not torch.is_grad_enabled():
                 if fused.available(self, x):
-                    return fused.block_forward(self, x)
+                    return fused.block_forward(self, x, out)
             elif _TRAIN_PATH == "fused" and fused.available(self, x):
                 from . import fused_train
                 return fused_train.block_forward(self, x)  # forward + backward of every stage on this library's kernels
-        return self.forward_compose(x)
+        y = self.forward_compose(x)
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
 
 
 # ----------------------------------------------------------------------------- U-Net pieces
@@ -340,6 +345,11 @@ class Upsampler(nn.Sequential):
         super().__init__(*m)
 
 
+def ops_mod():
+    from . import ops
+    return ops
+
+
 class _MamberUNet(nn.Module):
     """Shared 4-level encoder/decoder wiring (reference forward :610-638)."""
     VARIANT = "sisr"
@@ -385,6 +395,9 @@ class _MamberUNet(nn.Module):
         return self.up2_1(d2)
 
     def _trunk(self, inp_img):
+        from . import unet
+        if unet.enabled(inp_img) and inp_img.shape[2] % 8 == 0 and inp_img.shape[3] % 8 == 0:
+            return unet.trunk(self, inp_img)  # inference: the non-OSS convs / shuffles / concatenations on this library's kernels
         e1_in = self.patch_embed(inp_img)
         e1 = self.encoder_level1(e1_in)
         if self._lowres_chains > 1 and e1.is_cuda and not torch.is_grad_enabled():
@@ -409,10 +422,13 @@ class MambaSISR6(_MamberUNet):
     def forward(self, inp_img):
         feat, _ = self._trunk(inp_img)
         if feat.is_cuda and not torch.is_grad_enabled() and feat.dtype in (torch.float32, torch.bfloat16, torch.float16):
+            from . import unet
+            if unet.enabled(feat) and float(self.scale).is_integer() and feat.shape[1] % 8 == 0:
+                return self._tail_channels_last(feat, inp_img)  # "+ nearest-upsampled input" inside the last conv's store
             return self._tail_channels_last(feat) + F.interpolate(inp_img, scale_factor=self.scale, mode="nearest")
         return self.tail(feat) + F.interpolate(inp_img, scale_factor=self.scale, mode="nearest")
 
-    def _tail_channels_last(self, feat):
+    def _tail_channels_last(self, feat, inp_img=None):
         """inference: the SR tail (conv 3x3 -> PixelShuffle(2), twice, conv 3x3; reference common.py:45-60 and
         MambaSISR6_arch.py:607,640) on NHWC storage end to end -- the convs run on cuDNN's native layout and the pixel
         shuffles are this library's permutation kernel, instead of an NCHW<->NHWC transform either side of every conv
@@ -426,13 +442,21 @@ class MambaSISR6(_MamberUNet):
             self._tail_cl = cache
         wcl = cache[1]
         x = feat.contiguous(memory_format=torch.channels_last)
-        for m in list(self.tail[0]) + [self.tail[1]]:
+        mods = list(self.tail[0]) + [self.tail[1]]
+        for i, m in enumerate(mods):
+            if inp_img is not None and i == len(mods) - 1 and x.shape[1] % 8 == 0:
+                # conv_last + F.interpolate(inp_img, nearest) + add + NHWC -> NCHW: one kernel of this library (unet.py)
+                from . import unet
+                return unet.conv3x3(m, x.contiguous(memory_format=torch.channels_last), ops.CONV_ADD_NEAREST,
+                                    add=inp_img.to(x.dtype), add_scale=int(self.scale), nhwc=True)
             if isinstance(m, nn.Conv2d):
                 x = F.conv2d(x, wcl[id(m)], m.bias, m.stride, m.padding)
             elif isinstance(m, nn.PixelShuffle) and m.upscale_factor == 2 and x.shape[1] % 8 == 0:
                 x = ops.pixel_shuffle2_nhwc(x.contiguous(memory_format=torch.channels_last))
             else:
                 x = m(x)
+        if inp_img is not None:
+            return x.contiguous() + F.interpolate(inp_img, scale_factor=self.scale, mode="nearest")
         return x.contiguous()
 
 
@@ -456,6 +480,9 @@ class Mamber32(_MamberUNet):
         feat, e1_in = self._trunk(inp_img)
         if self.dual_pixel_task:
             return self.output(feat + self.skip_conv(e1_in))
+        from . import unet
+        if unet.enabled(feat):  # output conv + inp_img in one kernel
+            return unet.conv3x3(self.output, feat, ops_mod().CONV_ADD_NEAREST, add=inp_img.to(feat.dtype), add_scale=1)
         return self.output(feat) + inp_img
 
 

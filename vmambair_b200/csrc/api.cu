@@ -183,6 +183,24 @@ extern "C" int vmb_pixel_shuffle2_nhwc(const vmb_pixel_shuffle_args* a, void* st
     return pixel_shuffle_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int vmb_conv3x3(const vmb_conv3x3_args* a, void* stream) {
+    VMB_CHECK(a && a->x && a->w && a->out, "conv3x3: null pointer");
+    VMB_CHECK(dt_ok(a->dtype), "conv3x3: bad dtype");
+    VMB_CHECK(a->batch > 0 && a->batch <= 65535 && a->Cin > 0 && a->Cout > 0 && a->H > 0 && a->W > 0, "conv3x3: bad sizes");
+    VMB_CHECK(a->mode >= VMB_CONV_PLAIN && a->mode <= VMB_CONV_ADD_NEAREST, "conv3x3: unknown store mode %d", a->mode);
+    VMB_CHECK(a->mode != VMB_CONV_UNSHUFFLE2 || (a->H % 2 == 0 && a->W % 2 == 0), "conv3x3: PixelUnshuffle(2) needs even H, W");
+    VMB_CHECK(a->mode != VMB_CONV_SHUFFLE2 || a->Cout % 4 == 0, "conv3x3: PixelShuffle(2) needs Cout %% 4 == 0");
+    VMB_CHECK(a->mode != VMB_CONV_ADD_NEAREST || (a->add && a->add_scale >= 1 && a->H % a->add_scale == 0 && a->W % a->add_scale == 0),
+              "conv3x3: add image / scale missing or not dividing H, W");
+    VMB_CHECK(!a->in_nhwc || a->Cin % 8 == 0 || a->dtype == VMB_F32, "conv3x3: NHWC input needs Cin %% 8 == 0");
+    VMB_CHECK(aligned16(a->w) && (!a->in_nhwc || aligned16(a->x)), "conv3x3: weights (and an NHWC input) must be 16 B aligned");
+    VMB_CHECK((cdiv(a->Cout, 16)) <= 65535, "conv3x3: too many output channels");
+    Conv3Params p{a->x, a->w, a->bias, a->out, a->add, a->batch, a->Cin, a->Cout, a->H, a->W, a->in_nhwc, a->mode, a->add_scale,
+                  (a->Cout + 63) / 64 * 64, (a->Cin + 15) / 16 * 16,
+                  a->in_nhwc ? (int64_t)a->H * a->W * a->Cin : a->x_bs, a->x_cs, a->o_bs, a->o_cs, a->add_bs, a->add_cs};
+    return conv3x3_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int vmb_transpose_hw(const vmb_transpose_args* a, void* stream) {
     VMB_CHECK(a && a->x && a->out, "transpose: null pointer");
     VMB_CHECK(dt_ok(a->dtype) && a->planes > 0 && a->H > 0 && a->W > 0, "transpose: bad arguments");

@@ -1,0 +1,294 @@
+// Dense 3x3 convolution (stride 1, pad 1) of the U-Net's non-OSS stages: OverlapPatchEmbed.proj
+// (SRGAN/VmambaIR/archs/MambaSISR6_arch.py:520-528), Downsample = conv + PixelUnshuffle(2) (:533-541), Upsample = conv +
+// PixelShuffle(2) (:544-553), the SR tail's conv_last (+ the nearest-upsampled input image, :607,640) and Mamber32's output
+// conv.  One implicit GEMM per launch -- M = output channels, N = a tile of 8 x 16 output pixels, K = 9 taps x input
+// channels -- on mma.sync.m16n8k16 (the problems are 0.02-3 GFLOP: launch / latency bound, the tensor pipe is not the
+// limit), with everything the reference does around the conv as separate passes folded into the load or the store:
+//   * the input is read straight from NCHW (or NHWC) global memory into a [halo pixel][channel] shared-memory tile -- no
+//     layout-transform kernel in front of the conv;
+//   * the store applies PixelUnshuffle(2) / PixelShuffle(2) index arithmetic, writes into a channel slice of a wider tensor
+//     (the skip concatenation of the decoder: torch.cat never runs) or adds the nearest-neighbour up-sampled input image
+//     and emits NCHW -- no permutation / cat / interpolate / add kernels behind it.
+// fp32 I/O (parity mode) runs a SIMT FFMA kernel with the same tiling and the same store.
+#include "common.cuh"
+#include "oss_params.h"
+
+namespace vmb {
+namespace {
+
+constexpr int kTH = 8, kTW = 16;                      // output pixels of a CTA tile
+constexpr int kHaloW = kTW + 2, kHalo = (kTH + 2) * kHaloW;  // 10 x 18 input pixels
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+    const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    const int sz = valid ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], const void* smem) {
+    const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(s));
+}
+template <typename T> __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <> __device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <> __device__ __forceinline__ void mma16816<__half>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// One output element (b, m, y, x) of the convolution -> its place in `out` (see vmb_conv3x3_args.mode).
+template <typename T>
+__device__ __forceinline__ void conv_store(const Conv3Params& p, int b, int m, int y, int x, float v) {
+    if (p.bias) v += p.bias[m];
+    T* out = static_cast<T*>(p.out) + (int64_t)b * p.o_bs;
+    if (p.mode == VMB_CONV_PLAIN) {
+        out[(int64_t)m * p.o_cs + (int64_t)y * p.W + x] = from_f32<T>(v);
+    } else if (p.mode == VMB_CONV_UNSHUFFLE2) {  // nn.PixelUnshuffle(2): out[b, 4m + 2(y%2) + x%2, y/2, x/2]
+        const int oc = 4 * m + 2 * (y & 1) + (x & 1);
+        out[(int64_t)oc * p.o_cs + (int64_t)(y >> 1) * (p.W >> 1) + (x >> 1)] = from_f32<T>(v);
+    } else if (p.mode == VMB_CONV_SHUFFLE2) {    // nn.PixelShuffle(2): out[b, m/4, 2y + (m/2)%2, 2x + m%2]
+        out[(int64_t)(m >> 2) * p.o_cs + (int64_t)(2 * y + ((m >> 1) & 1)) * (2 * p.W) + 2 * x + (m & 1)] = from_f32<T>(v);
+    } else {                                      // VMB_CONV_ADD_NEAREST: + add[b, m, y/s, x/s]
+        const T* add = static_cast<const T*>(p.add) + (int64_t)b * p.add_bs + (int64_t)m * p.add_cs;
+        v += to_f32<T>(add[(int64_t)(y / p.add_scale) * (p.W / p.add_scale) + x / p.add_scale]);
+        out[(int64_t)m * p.o_cs + (int64_t)y * p.W + x] = from_f32<T>(v);
+    }
+}
+
+// ---- 16-bit I/O: implicit GEMM on mma.sync ---------------------------------------------------------------------------------
+// Shared memory per stage: A = weights of the K chunk [9 taps][MT rows][KC] and B = input halo tile [180 pixels][KC], rows
+// padded by 16 B (row pitch 48 B at KC = 16, 80 B at KC = 32: the eight 16 B rows of an ldmatrix phase fall into distinct
+// bank groups).  Two stages: the weights of chunk k+1 arrive by cp.async and its input pixels through registers (NCHW: the
+// [channel][pixel] -> [pixel][channel] transposition happens in the register -> shared store) while chunk k is multiplied.
+template <typename T, int MT, int KC, bool NHWC>
+__global__ void __launch_bounds__(128) conv3x3_mma_kernel(const Conv3Params p) {
+    pdl_trigger();
+    constexpr int PITCH = KC * 2 + 16;            // bytes per smem row
+    constexpr int A_BYTES = 9 * MT * PITCH, B_BYTES = kHalo * PITCH, STAGE = A_BYTES + B_BYTES;
+    constexpr int MI = MT / 16;
+    constexpr int KH = KC / 8;                    // 16 B pieces per row
+    constexpr int NPAIR = KC / 2;                 // channel pairs per chunk
+    constexpr int BREG = (NPAIR * kHalo + 127) / 128;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles_x = (p.W + kTW - 1) / kTW;
+    const int x0 = (blockIdx.x % tiles_x) * kTW, y0 = (blockIdx.x / tiles_x) * kTH;
+    const int m0 = blockIdx.y * MT, b = blockIdx.z;
+    const T* __restrict__ xin = static_cast<const T*>(p.x) + (int64_t)b * p.x_bs;
+    const T* __restrict__ wgt = static_cast<const T*>(p.w);
+    const int nchunk = (p.Cin + KC - 1) / KC;
+
+    float acc[MI][4][4];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+
+    auto stage_A = [&](int kc, int s) {  // weights are static parameters: may be fetched before pdl_wait()
+        unsigned char* A = smem + s * STAGE;
+        for (int i = tid; i < 9 * MT * KH; i += 128) {
+            const int piece = i % KH, row = (i / KH) % MT, tap = i / (KH * MT);
+            const T* src = wgt + ((int64_t)(tap * p.Mpad + m0 + row)) * p.Kpad + kc * KC + piece * 8;
+            cp_async16(A + (tap * MT + row) * PITCH + piece * 16, src, kc * KC + piece * 8 < p.Kpad);
+        }
+    };
+    uint32_t breg[BREG];
+    auto load_B = [&](int kc, int s) {
+        if constexpr (NHWC) {
+            unsigned char* Bs = smem + s * STAGE + A_BYTES;
+            for (int i = tid; i < kHalo * KH; i += 128) {
+                const int piece = i % KH, hp = i / KH;
+                const int gy = y0 - 1 + hp / kHaloW, gx = x0 - 1 + hp % kHaloW, c = kc * KC + piece * 8;
+                const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W && c < p.Cin;
+                const T* src = ok ? xin + ((int64_t)gy * p.W + gx) * p.Cin + c : xin;
+                cp_async16(Bs + hp * PITCH + piece * 16, src, ok);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < BREG; ++j) {
+                const int i = tid + 128 * j;
+                const int hp = i % kHalo, cp = i / kHalo;
+                const int gy = y0 - 1 + hp / kHaloW, gx = x0 - 1 + hp % kHaloW, c = kc * KC + 2 * cp;
+                uint32_t v = 0;
+                if (cp < NPAIR && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W && c < p.Cin) {
+                    const T* src = xin + (int64_t)c * p.x_cs + (int64_t)gy * p.W + gx;
+                    const uint32_t lo = *reinterpret_cast<const unsigned short*>(src);
+                    const uint32_t hi = c + 1 < p.Cin ? *reinterpret_cast<const unsigned short*>(src + p.x_cs) : 0u;
+                    v = lo | (hi << 16);
+                }
+                breg[j] = v;
+            }
+        }
+    };
+    auto store_B = [&](int s) {
+        if constexpr (!NHWC) {
+            unsigned char* Bs = smem + s * STAGE + A_BYTES;
+#pragma unroll
+            for (int j = 0; j < BREG; ++j) {
+                const int i = tid + 128 * j;
+                const int hp = i % kHalo, cp = i / kHalo;
+                if (cp < NPAIR) *reinterpret_cast<uint32_t*>(Bs + hp * PITCH + cp * 4) = breg[j];
+            }
+        }
+    };
+
+    stage_A(0, 0);
+    pdl_wait();  // the activations are the preceding kernel's output
+    load_B(0, 0);
+    cp_async_commit();
+    store_B(0);
+
+    // fragment addressing (warp-uniform bases + per-lane offsets)
+    const int trow0 = 2 * warp;                         // this warp's two tile rows
+    const int a_lane = ((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (lane >> 4) * 16;
+    const int b_lane = (((lane >> 4) & 1) * 8 + (lane & 7)) * PITCH + ((lane >> 3) & 1) * 16;
+
+    for (int kc = 0; kc < nchunk; ++kc) {
+        const int s = kc & 1;
+        if (kc + 1 < nchunk) {
+            stage_A(kc + 1, s ^ 1);
+            load_B(kc + 1, s ^ 1);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const unsigned char* A = smem + s * STAGE;
+        const unsigned char* Bs = A + A_BYTES;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap % 3;
+#pragma unroll
+            for (int ks = 0; ks < KC / 16; ++ks) {
+                uint32_t bf[2][4];
+#pragma unroll
+                for (int r = 0; r < 2; ++r)  // tile row trow0 + r: n-tiles 2r (columns 0-7) and 2r+1 (columns 8-15)
+                    ldsm4(bf[r], Bs + ((trow0 + r + dy) * kHaloW + dx) * PITCH + b_lane + ks * 32);
+#pragma unroll
+                for (int mi = 0; mi < MI; ++mi) {
+                    uint32_t af[4];
+                    ldsm4(af, A + (tap * MT + mi * 16) * PITCH + a_lane + ks * 32);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mma16816<T>(acc[mi][j], af, bf[j >> 1][(j & 1) * 2], bf[j >> 1][(j & 1) * 2 + 1]);
+                }
+            }
+        }
+        if (kc + 1 < nchunk) store_B(s ^ 1);
+        __syncthreads();
+    }
+
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int m = m0 + mi * 16 + g + (e >> 1) * 8;
+                const int y = y0 + trow0 + (j >> 1), x = x0 + (j & 1) * 8 + 2 * t + (e & 1);
+                if (m < p.Cout && y < p.H && x < p.W) conv_store<T>(p, b, m, y, x, acc[mi][j][e]);
+            }
+}
+
+// ---- fp32 I/O (parity mode): direct FFMA convolution, one output pixel x 16 output channels per thread ---------------------
+template <typename T, bool NHWC>
+__global__ void __launch_bounds__(128) conv3x3_simt_kernel(const Conv3Params p) {
+    pdl_trigger();
+    constexpr int MT = 16, KC = 8;
+    __shared__ float sx[KC][kTH + 2][kHaloW + 1];
+    __shared__ float sw[9][KC][MT];
+    const int tid = threadIdx.x, tx = tid % kTW, ty = tid / kTW;
+    const int tiles_x = (p.W + kTW - 1) / kTW;
+    const int x0 = (blockIdx.x % tiles_x) * kTW, y0 = (blockIdx.x / tiles_x) * kTH;
+    const int m0 = blockIdx.y * MT, b = blockIdx.z;
+    const T* __restrict__ xin = static_cast<const T*>(p.x) + (int64_t)b * p.x_bs;
+    const T* __restrict__ wgt = static_cast<const T*>(p.w);
+    float acc[MT];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) acc[i] = 0.f;
+    pdl_wait();
+    for (int c0 = 0; c0 < p.Cin; c0 += KC) {
+        for (int i = tid; i < KC * kHalo; i += 128) {
+            const int hp = i % kHalo, cc = i / kHalo;
+            const int hy = hp / kHaloW, hx = hp % kHaloW, gy = y0 - 1 + hy, gx = x0 - 1 + hx, c = c0 + cc;
+            float v = 0.f;
+            if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W && c < p.Cin)
+                v = to_f32<T>(NHWC ? xin[((int64_t)gy * p.W + gx) * p.Cin + c] : xin[(int64_t)c * p.x_cs + (int64_t)gy * p.W + gx]);
+            sx[cc][hy][hx] = v;
+        }
+        for (int i = tid; i < 9 * KC * MT; i += 128) {
+            const int mm = i % MT, cc = (i / MT) % KC, tap = i / (MT * KC);
+            const int c = c0 + cc;
+            sw[tap][cc][mm] = c < p.Kpad ? to_f32<T>(wgt[((int64_t)(tap * p.Mpad + m0 + mm)) * p.Kpad + c]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int cc = 0; cc < KC; ++cc)
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const float v = sx[cc][ty + tap / 3][tx + tap % 3];
+#pragma unroll
+                for (int mm = 0; mm < MT; ++mm) acc[mm] = fmaf(sw[tap][cc][mm], v, acc[mm]);
+            }
+        __syncthreads();
+    }
+    const int y = y0 + ty, x = x0 + tx;
+    if (y < p.H && x < p.W)
+#pragma unroll
+        for (int mm = 0; mm < MT; ++mm)
+            if (m0 + mm < p.Cout) conv_store<T>(p, b, m0 + mm, y, x, acc[mm]);
+}
+
+template <typename T, int MT, int KC, bool NHWC>
+int launch_mma(const Conv3Params& p, cudaStream_t stream) {
+    constexpr int PITCH = KC * 2 + 16;
+    constexpr int SMEM = 2 * (9 * MT * PITCH + kHalo * PITCH);
+    auto kern = conv3x3_mma_kernel<T, MT, KC, NHWC>;
+    static bool attr_set = false;  // idempotent: a race only repeats the call
+    if (SMEM > 48 * 1024 && !attr_set) {
+        VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr_set = true;
+    }
+    const dim3 grid(cdiv(p.W, kTW) * cdiv(p.H, kTH), cdiv(p.Cout, MT), p.B);
+    VMB_CUDA(launch_pdl(kern, grid, dim3(128), SMEM, stream, p));
+    return VMB_OK;
+}
+
+template <typename T>
+int launch_16(const Conv3Params& p, cudaStream_t stream) {
+    const int tiles = cdiv(p.W, kTW) * cdiv(p.H, kTH) * p.B;
+    if (p.in_nhwc) {
+        if (p.Cout <= 16) return launch_mma<T, 16, 16, true>(p, stream);
+        return launch_mma<T, 64, 16, true>(p, stream);
+    }
+    // few CTAs and a long reduction (the low-resolution levels): 32-channel chunks halve the number of exposed load latencies
+    const bool deep = p.Cin >= 96 && tiles * cdiv(p.Cout, 64) <= 148;
+    if (p.Cout <= 16) return launch_mma<T, 16, 16, false>(p, stream);
+    if (p.Cout <= 32 || (deep && p.Cout <= 96)) return deep ? launch_mma<T, 32, 32, false>(p, stream) : launch_mma<T, 32, 16, false>(p, stream);
+    return deep ? launch_mma<T, 64, 32, false>(p, stream) : launch_mma<T, 64, 16, false>(p, stream);
+}
+
+}  // namespace
+
+int conv3x3_launch(const Conv3Params& p, int dtype, cudaStream_t stream) {
+    if (dtype == VMB_BF16) return launch_16<__nv_bfloat16>(p, stream);
+    if (dtype == VMB_F16) return launch_16<__half>(p, stream);
+    const dim3 grid(cdiv(p.W, kTW) * cdiv(p.H, kTH), cdiv(p.Cout, 16), p.B);
+    if (p.in_nhwc) {
+        VMB_CUDA(launch_pdl(conv3x3_simt_kernel<float, true>, grid, dim3(128), 0, stream, p));
+    } else {
+        VMB_CUDA(launch_pdl(conv3x3_simt_kernel<float, false>, grid, dim3(128), 0, stream, p));
+    }
+    return VMB_OK;
+}
+
+}  // namespace vmb

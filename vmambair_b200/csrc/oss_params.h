@@ -48,6 +48,14 @@ struct ChannelParams {
     float* c_out;
     int B, C, dc, Rc, N;
 };
+struct Conv3Params {
+    const void* x; const void* w; const float* bias; void* out; const void* add;
+    int B, Cin, Cout, H, W;
+    int in_nhwc, mode, add_scale;
+    int Mpad, Kpad;  // packed weights: [9 taps][Mpad][Kpad], Mpad % 64 == 0, Kpad % 16 == 0, zero padded
+    int64_t x_bs, x_cs, o_bs, o_cs, add_bs, add_cs;
+};
+int conv3x3_launch(const Conv3Params& p, int dtype, cudaStream_t stream);
 int pixlin_launch(const PixlinParams& p, int dtype, int out_dtype, cudaStream_t stream);
 bool pixlin_tc_applicable(const PixlinParams& p, int dtype, int out_dtype);
 int pixlin_tc_launch(const PixlinParams& p, int dtype, cudaStream_t stream);

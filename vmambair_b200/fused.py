@@ -111,7 +111,9 @@ def _prepare(block, dtype, device):
 
 
 @torch.no_grad()
-def block_forward(block, x: torch.Tensor) -> torch.Tensor:
+def block_forward(block, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """out: optional (B,C,H,W) destination with dense planes -- e.g. a channel slice of the decoder's concatenation buffer
+    (unet.py): the block's last kernel stores there and torch.cat never runs."""
     B, C, H, W = x.shape
     L = H * W
     c = _prepare(block, x.dtype, x.device)
@@ -130,7 +132,7 @@ def block_forward(block, x: torch.Tensor) -> torch.Tensor:
         ys = ops.selective_scan_fwd_grouped([s[0] for s in src], [s[1][:, :C] for s in src], [s[1][:, C:C + N] for s in src],
                                             [s[1][:, C + N:] for s in src], [0, 0, 1, 1], c["A"], c["Ds"], c["dt_bias"], True)
         y2, pooled = ops.merge_norm_gate(ys, xz[:, C:], c["on_w"], c["on_b"], C, H, W, in_place_order=True)
-        return _block_tail(c, x3, y2, pooled, B, C, H, W)
+        return _block_tail(c, x3, y2, pooled, B, C, H, W, out)
     # delta (dt_proj o x_proj), B, C of the four directions from one GEMM on the un-permuted x
     dbl = ops.pixlin(xc, c["w_big"], static_w=True)  # (B, 4*(C+2N), L)
     dbl4 = dbl.view(B, 4, C + 2 * N, L)
@@ -140,14 +142,18 @@ def block_forward(block, x: torch.Tensor) -> torch.Tensor:
     ys, _ = ops.selective_scan_fwd(xs.view(B, 4 * C, L), dts.view(B, 4 * C, L), c["A"], bc[:, :, :N], bc[:, :, N:], c["Ds"],
                                    c["dt_bias"], True, need_ckpt=False)
     y2, pooled = ops.merge_norm_gate(ys.view(B, 4, C, L), xz[:, C:], c["on_w"], c["on_b"], C, H, W)
-    return _block_tail(c, x3, y2, pooled, B, C, H, W)
+    return _block_tail(c, x3, y2, pooled, B, C, H, W, out)
 
 
-def _block_tail(c, x3, y2, pooled, B, C, H, W):
+def _block_tail(c, x3, y2, pooled, B, C, H, W, dst=None):
     L = H * W
     cg = ops.channel_branch(pooled, 1.0 / L, c["ch"], C)
     x1 = ops.pixlin(y2, c["w_out"], c["b_out"], residual=x3, gate=cg, gate_mode=c["gate_mode"], static_w=True)
     t = ops.pixlin(x1, c["w_pin"], c["b_pin"], ln=c["ln2"], static_w=True)
     g = ops.dwconv3x3(t, c["fdw"], c["fdw_b"], c["h"], H, W, 1)
+    if dst is not None:
+        assert dst.shape == (B, C, H, W) and dst.stride(3) == 1 and dst.stride(2) == W and dst.stride(1) == L
+        ops.pixlin(g, c["w_pout"], c["b_pout"], residual=x1, static_w=True, out=dst.view(B, C, L))
+        return dst
     out = ops.pixlin(g, c["w_pout"], c["b_pout"], residual=x1, static_w=True)
     return out.view(B, C, H, W)

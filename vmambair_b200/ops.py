@@ -224,6 +224,49 @@ def pixel_shuffle2_nhwc(x):
     return out
 
 
+CONV_PLAIN, CONV_UNSHUFFLE2, CONV_SHUFFLE2, CONV_ADD_NEAREST = 0, 1, 2, 3
+
+
+def pack_conv3x3_weight(w: torch.Tensor, dtype) -> torch.Tensor:
+    """nn.Conv2d weight (Cout, Cin, 3, 3) -> the kernel layout [tap = 3 ky + kx][Cout rounded up to 64][Cin rounded up to 16], zero
+    padded, in the I/O dtype (include/vmambair_b200.h, vmb_conv3x3)."""
+    Cout, Cin = w.shape[0], w.shape[1]
+    assert w.shape[2:] == (3, 3)
+    out = torch.zeros((9, (Cout + 63) // 64 * 64, (Cin + 15) // 16 * 16), dtype=dtype, device=w.device)
+    out[:, :Cout, :Cin] = w.detach().permute(2, 3, 0, 1).reshape(9, Cout, Cin).to(dtype)
+    return out
+
+
+def conv3x3(x, wp, bias, c_out, mode=CONV_PLAIN, out=None, add=None, add_scale=1, nhwc=False):
+    """Dense 3x3 conv (stride 1, pad 1) with the PixelUnshuffle(2) / PixelShuffle(2) / channel-slice / "+ nearest-upsampled image"
+    store folded in.  x: (B, Cin, H, W), NCHW view with dense planes (any batch / channel stride) or, nhwc=True, channels_last
+    contiguous.  wp: pack_conv3x3_weight(...).  bias: fp32 (c_out) or None.  out: optional NCHW destination with dense planes (e.g.
+    a channel slice of the decoder's concatenation buffer).  add (mode CONV_ADD_NEAREST): (B, c_out, H/s, W/s), x.dtype."""
+    B, Cin, H, W = x.shape
+    if nhwc:
+        assert x.is_contiguous(memory_format=torch.channels_last)
+        x_bs, x_cs = H * W * Cin, 1
+    else:
+        assert x.stride(3) == 1 and x.stride(2) == W, "conv3x3: NCHW input planes must be dense"
+        x_bs, x_cs = x.stride(0), x.stride(1)
+    assert wp.dtype == x.dtype and wp.is_contiguous() and wp.shape == (9, (c_out + 63) // 64 * 64, (Cin + 15) // 16 * 16)
+    shape = {CONV_PLAIN: (B, c_out, H, W), CONV_UNSHUFFLE2: (B, 4 * c_out, H // 2, W // 2),
+             CONV_SHUFFLE2: (B, c_out // 4, 2 * H, 2 * W), CONV_ADD_NEAREST: (B, c_out, H, W)}[mode]
+    if out is None:
+        out = torch.empty(shape, dtype=x.dtype, device=x.device)
+    assert tuple(out.shape) == shape and out.dtype == x.dtype and out.stride(3) == 1 and out.stride(2) == shape[3]
+    add_bs = add_cs = 0
+    if mode == CONV_ADD_NEAREST:
+        assert add is not None and add.dtype == x.dtype and add.shape == (B, c_out, H // add_scale, W // add_scale)
+        add = add.contiguous()
+        add_bs, add_cs = add.stride(0), add.stride(1)
+    a = _lib.Conv3x3Args(_ptr(x), _ptr(wp), _ptr(bias), _ptr(out), _ptr(add) if mode == CONV_ADD_NEAREST else None,
+                         B, Cin, c_out, H, W, int(nhwc), mode, add_scale, x_bs, x_cs, out.stride(0), out.stride(1), add_bs, add_cs,
+                         _DT[x.dtype])
+    _run("vmb_conv3x3", a, x, "conv3x3")
+    return out
+
+
 def transpose_hw(x, H, W):
     """x: (B, C, H*W) contiguous -> (B, C, W*H) with every plane transposed."""
     assert x.is_contiguous()
