@@ -13,19 +13,25 @@ import torch.nn.functional as F
 from vmambair_b200 import ops
 
 
-def timeit(fn, n=30):
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    for _ in range(3):
-        fn()
-    ts = []
-    for _ in range(n):
-        flush.zero_()
-        s, e = torch.cuda.Event(True), torch.cuda.Event(True)
-        s.record()
-        fn()
-        e.record()
-        torch.cuda.synchronize()
-        ts.append(s.elapsed_time(e) * 1e3)
+def timeit(fn, n=10, reps=20):
+    """device time per call inside a CUDA graph of `reps` back-to-back calls (no host launch latency in the number; warm L2)"""
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for _ in range(3):
+            fn()
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(reps):
+                fn()
+        ts = []
+        for _ in range(n):
+            s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+            s.record(st)
+            g.replay()
+            e.record(st)
+            st.synchronize()
+            ts.append(s.elapsed_time(e) * 1e3 / reps)
     ts.sort()
     return ts[len(ts) // 2]
 

@@ -4,14 +4,15 @@
 // conv.  One implicit GEMM per launch -- M = output channels, N = a tile of 8 x 16 output pixels, K = 9 taps x input
 // channels -- on mma.sync.m16n8k16 (the problems are 0.02-3 GFLOP: launch / latency bound, the tensor pipe is not the
 // limit), with everything the reference does around the conv as separate passes folded into the load or the store:
-//   * the input is read straight from NCHW (or NHWC) global memory into a [halo pixel][channel] shared-memory tile -- no
-//     layout-transform kernel in front of the conv;
+//   * the input halo tile comes straight from NCHW (or NHWC) global memory as TMA boxes (cp.async.bulk.tensor, borders = the
+//     TMA's zero fill) -- no layout-transform kernel in front of the conv;
 //   * the store applies PixelUnshuffle(2) / PixelShuffle(2) index arithmetic, writes into a channel slice of a wider tensor
 //     (the skip concatenation of the decoder: torch.cat never runs) or adds the nearest-neighbour up-sampled input image
 //     and emits NCHW -- no permutation / cat / interpolate / add kernels behind it.
 // fp32 I/O (parity mode) runs a SIMT FFMA kernel with the same tiling and the same store.
 #include "common.cuh"
 #include "oss_params.h"
+#include "tma.cuh"
 
 namespace vmb {
 namespace {
@@ -61,13 +62,14 @@ __device__ __forceinline__ void conv_store(const Conv3Params& p, int b, int m, i
     }
 }
 
-// ---- 16-bit I/O: implicit GEMM on mma.sync ---------------------------------------------------------------------------------
+// ---- 16-bit I/O, any NCHW geometry (ragged W, unaligned views): implicit GEMM on mma.sync ------------------------------------
 // Shared memory per stage: A = weights of the K chunk [9 taps][MT rows][KC] and B = input halo tile [180 pixels][KC], rows
-// padded by 16 B (row pitch 48 B at KC = 16, 80 B at KC = 32: the eight 16 B rows of an ldmatrix phase fall into distinct
-// bank groups).  Two stages: the weights of chunk k+1 arrive by cp.async and its input pixels through registers (NCHW: the
-// [channel][pixel] -> [pixel][channel] transposition happens in the register -> shared store) while chunk k is multiplied.
+// padded by 16 B (row pitch 48 B at KC = 16: the eight 16 B rows of an ldmatrix phase fall into distinct bank groups).  Two
+// stages: the weights of chunk k+1 arrive by cp.async and its input pixels through registers (the [channel][pixel] ->
+// [pixel][channel] transposition happens in the register -> shared store) while chunk k is multiplied.  The fallback of
+// conv3x3_pipe_kernel below, which needs 16 B-aligned rows.
 template <typename T, int MT, int KC, bool NHWC>
-__global__ void __launch_bounds__(128) conv3x3_mma_kernel(const Conv3Params p) {
+__global__ void __launch_bounds__(128) conv3x3_generic_kernel(const Conv3Params p) {
     pdl_trigger();
     constexpr int PITCH = KC * 2 + 16;            // bytes per smem row
     constexpr int A_BYTES = 9 * MT * PITCH, B_BYTES = kHalo * PITCH, STAGE = A_BYTES + B_BYTES;
@@ -199,6 +201,149 @@ __global__ void __launch_bounds__(128) conv3x3_mma_kernel(const Conv3Params p) {
             }
 }
 
+// ---- 16-bit I/O, aligned geometry (W % 8 == 0, 16 B-aligned planes: every site of the networks): TMA-staged pipeline ------------
+// One elected thread issues two cp.async.bulk.tensor boxes per 16-channel chunk into a STAGES-deep ring (completion on an
+// mbarrier per stage): the weights [9 taps x MT rows][16] with the 32 B swizzle (conflict-free ldmatrix on 32 B rows) and the
+// input halo tile -- NHWC input: box (16 c, 18 x, 10 y), swizzled, consumed by ldmatrix as it lands; NCHW input: box (32 x,
+// 10 y, 16 c) = channel planes as they lie in global memory, re-laid once per chunk by all threads into the [pixel][channel]
+// tile the fragments want (the [c][p] -> [p][c] step costs ~12 packed stores per thread and chunk; assembling fragments from
+// the planar tile tap by tap costs four times that).  Image borders, the ragged last tile and channels >= Cin are the TMA's
+// out-of-bounds zero fill: the kernel has no address arithmetic or predicates on the load side at all.
+constexpr int kRawW = 32, kRawX = 8;                     // NCHW box: 32 pixels (64 B rows) starting at x0 - 8: a box must start on
+                                                         // a 16 B boundary of global memory (x0 - 1 raises an illegal-instruction fault)
+constexpr int kRawPlane = (kTH + 2) * kRawW * 2;         // bytes per channel plane of the raw box
+constexpr int kBtPitch = 48;                             // [pixel][16 channels] tile, rows padded to 48 B
+
+template <int MT, bool NHWC> struct TmaConvCfg {
+    static constexpr int A_BYTES = 9 * MT * 32;
+    static constexpr int B_BYTES = NHWC ? kHalo * 32 : 16 * kRawPlane;
+    static constexpr int STAGE = (A_BYTES + B_BYTES + 255) / 256 * 256;
+    static constexpr int BT_BYTES = NHWC ? 0 : kHalo * kBtPitch;
+    static constexpr int smem(int stages) { return stages * STAGE + BT_BYTES + 8 * stages + 1024; }
+};
+
+template <typename T, int MT, int STAGES, bool NHWC>
+__global__ void __launch_bounds__(128) conv3x3_tma_kernel(const Conv3Params p, const __grid_constant__ CUtensorMap mapW,
+                                                          const __grid_constant__ CUtensorMap mapX) {
+    pdl_trigger();
+    using Cfg = TmaConvCfg<MT, NHWC>;
+    constexpr int MI = MT / 16;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* Bt = smem + STAGES * Cfg::STAGE;
+    uint64_t* full = reinterpret_cast<uint64_t*>(Bt + Cfg::BT_BYTES);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles_x = (p.W + kTW - 1) / kTW;
+    const int x0 = (blockIdx.x % tiles_x) * kTW, y0 = (blockIdx.x / tiles_x) * kTH;
+    const int m0 = blockIdx.y * MT, b = blockIdx.z;
+    const int nchunk = (p.Cin + 15) / 16;
+
+    if (tid == 0) {
+        if (p.dbg & 1) {
+            tma_prefetch_desc(&mapW);
+            tma_prefetch_desc(&mapX);
+        }
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbarrier_init(&full[s], 1);
+        mbarrier_init_fence();
+    }
+    __syncthreads();
+    pdl_wait();  // the activations are the preceding kernel's output
+    auto issue = [&](int kc, int s) {
+        unsigned char* A = smem + s * Cfg::STAGE;
+        mbarrier_expect_tx(&full[s], ((p.dbg & 4) ? 0 : Cfg::A_BYTES) + ((p.dbg & 8) ? 0 : Cfg::B_BYTES));
+        if (!(p.dbg & 4)) tma_load_4d(A, &mapW, &full[s], kc * 16, m0, 0, 0);
+        if (!(p.dbg & 8)) {
+            if constexpr (NHWC) tma_load_4d(A + Cfg::A_BYTES, &mapX, &full[s], kc * 16, x0 - 1, y0 - 1, b);
+            else tma_load_4d(A + Cfg::A_BYTES, &mapX, &full[s], x0 - kRawX, y0 - 1, kc * 16, b);
+        }
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+            if (s < nchunk) issue(s, s);
+    }
+
+    float acc[MI][4][4];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+
+    const int trow0 = 2 * warp;
+    const int g = lane >> 2, t = lane & 3;
+    // A: row r of the swizzled [rows][32 B] tile holds its 16 B half q at ((q ^ ((r >> 2) & 1)) << 4)
+    const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int a_lane = a_row * 32 + (((lane >> 4) ^ ((a_row >> 2) & 1)) << 4);
+    const int bt_lane = (((lane >> 4) & 1) * 8 + (lane & 7)) * kBtPitch + ((lane >> 3) & 1) * 16;  // [pixel][channel] tile (NCHW)
+    const int bq = (lane >> 3) & 1, bpix = ((lane >> 4) & 1) * 8 + (lane & 7);                     // swizzled halo tile (NHWC)
+    bool jok[4];  // n-tiles inside the image (warp-uniform): the others are skipped
+#pragma unroll
+    for (int j = 0; j < 4; ++j) jok[j] = (y0 + trow0 + (j >> 1) < p.H) && (x0 + (j & 1) * 8 < p.W);
+
+    for (int kc = 0; kc < nchunk; ++kc) {
+        const int slot = kc % STAGES;
+        mbarrier_wait(&full[slot], (kc / STAGES) & 1);
+        const unsigned char* A = smem + slot * Cfg::STAGE;
+        const unsigned char* Braw = A + Cfg::A_BYTES;
+        if constexpr (!NHWC) {
+            // [16 planes][10][32] -> [180 pixels][16 channels]: two channels of one pixel per packed 32-bit store
+#pragma unroll
+            for (int j = 0; j < (8 * kHalo + 127) / 128; ++j) {
+                const int i = tid + 128 * j;
+                const int hp = i % kHalo, cp = i / kHalo;
+                if (cp < 8) {
+                    const unsigned char* src = Braw + 2 * cp * kRawPlane + (hp / kHaloW) * (kRawW * 2) + (hp % kHaloW + kRawX - 1) * 2;
+                    const uint32_t v = *reinterpret_cast<const unsigned short*>(src) |
+                                       (uint32_t(*reinterpret_cast<const unsigned short*>(src + kRawPlane)) << 16);
+                    *reinterpret_cast<uint32_t*>(Bt + hp * kBtPitch + cp * 4) = v;
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap % 3;
+            uint32_t bf[2][4];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {  // tile row trow0 + r: n-tiles 2r (columns 0-7) and 2r+1 (columns 8-15)
+                if constexpr (NHWC) {
+                    const int hp = (trow0 + r + dy) * kHaloW + dx + bpix;
+                    ldsm4(bf[r], Braw + hp * 32 + ((bq ^ ((hp >> 2) & 1)) << 4));
+                } else {
+                    ldsm4(bf[r], Bt + ((trow0 + r + dy) * kHaloW + dx) * kBtPitch + bt_lane);
+                }
+            }
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi) {
+                uint32_t af[4];
+                ldsm4(af, A + (tap * MT + mi * 16) * 32 + a_lane);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (jok[j]) mma16816<T>(acc[mi][j], af, bf[j >> 1][(j & 1) * 2], bf[j >> 1][(j & 1) * 2 + 1]);
+            }
+        }
+        __syncthreads();  // every warp is done with this stage (and with Bt)
+        if (tid == 0 && kc + STAGES < nchunk) {
+            fence_proxy_async();  // the stage was read through the generic proxy; the refill writes through the async proxy
+            issue(kc + STAGES, slot);
+        }
+    }
+
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int m = m0 + mi * 16 + g + (e >> 1) * 8;
+                const int y = y0 + trow0 + (j >> 1), x = x0 + (j & 1) * 8 + 2 * t + (e & 1);
+                if (m < p.Cout && y < p.H && x < p.W) conv_store<T>(p, b, m, y, x, acc[mi][j][e]);
+            }
+}
+
 // ---- fp32 I/O (parity mode): direct FFMA convolution, one output pixel x 16 output channels per thread ---------------------
 template <typename T, bool NHWC>
 __global__ void __launch_bounds__(128) conv3x3_simt_kernel(const Conv3Params p) {
@@ -248,11 +393,11 @@ __global__ void __launch_bounds__(128) conv3x3_simt_kernel(const Conv3Params p) 
             if (m0 + mm < p.Cout) conv_store<T>(p, b, m0 + mm, y, x, acc[mm]);
 }
 
-template <typename T, int MT, int KC, bool NHWC>
-int launch_mma(const Conv3Params& p, cudaStream_t stream) {
-    constexpr int PITCH = KC * 2 + 16;
+template <typename T, int MT>
+int launch_generic(const Conv3Params& p, cudaStream_t stream) {
+    constexpr int PITCH = 16 * 2 + 16;
     constexpr int SMEM = 2 * (9 * MT * PITCH + kHalo * PITCH);
-    auto kern = conv3x3_mma_kernel<T, MT, KC, NHWC>;
+    auto kern = conv3x3_generic_kernel<T, MT, 16, false>;
     static bool attr_set = false;  // idempotent: a race only repeats the call
     if (SMEM > 48 * 1024 && !attr_set) {
         VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -263,25 +408,66 @@ int launch_mma(const Conv3Params& p, cudaStream_t stream) {
     return VMB_OK;
 }
 
-template <typename T>
-int launch_16(const Conv3Params& p, cudaStream_t stream) {
-    const int tiles = cdiv(p.W, kTW) * cdiv(p.H, kTH) * p.B;
-    if (p.in_nhwc) {
-        if (p.Cout <= 16) return launch_mma<T, 16, 16, true>(p, stream);
-        return launch_mma<T, 64, 16, true>(p, stream);
+template <typename T, int MT, int STAGES, bool NHWC>
+int launch_tma(const Conv3Params& p, int dtype, cudaStream_t stream) {
+    using Cfg = TmaConvCfg<MT, NHWC>;
+    constexpr int SMEM = Cfg::smem(STAGES);
+    static_assert(SMEM <= 227 * 1024, "conv3x3: stage ring exceeds shared memory");
+    CUtensorMap mapW, mapX;
+    {
+        const uint64_t dims[4] = {(uint64_t)p.Kpad, (uint64_t)p.Mpad, 9, 1};
+        const int64_t str[3] = {p.Kpad, (int64_t)p.Mpad * p.Kpad, (int64_t)9 * p.Mpad * p.Kpad};
+        const uint32_t box[4] = {16, (uint32_t)MT, 9, 1};
+        const int rc = make_tmap_4d(&mapW, dtype, p.w, dims, str, box, (p.dbg & 2) ? 0 : 1);
+        if (rc != VMB_OK) return rc;
     }
-    // few CTAs and a long reduction (the low-resolution levels): 32-channel chunks halve the number of exposed load latencies
-    const bool deep = p.Cin >= 96 && tiles * cdiv(p.Cout, 64) <= 148;
-    if (p.Cout <= 16) return launch_mma<T, 16, 16, false>(p, stream);
-    if (p.Cout <= 32 || (deep && p.Cout <= 96)) return deep ? launch_mma<T, 32, 32, false>(p, stream) : launch_mma<T, 32, 16, false>(p, stream);
-    return deep ? launch_mma<T, 64, 32, false>(p, stream) : launch_mma<T, 64, 16, false>(p, stream);
+    if (NHWC) {
+        const uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
+        const int64_t str[3] = {p.Cin, (int64_t)p.W * p.Cin, (int64_t)p.H * p.W * p.Cin};
+        const uint32_t box[4] = {16, (uint32_t)kHaloW, (uint32_t)(kTH + 2), 1};
+        const int rc = make_tmap_4d(&mapX, dtype, p.x, dims, str, box, (p.dbg & 2) ? 0 : 1);
+        if (rc != VMB_OK) return rc;
+    } else {
+        const uint64_t dims[4] = {(uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.Cin, (uint64_t)p.B};
+        const int64_t str[3] = {p.W, p.x_cs, p.x_bs};
+        const uint32_t box[4] = {(uint32_t)kRawW, (uint32_t)(kTH + 2), 16, 1};
+        const int rc = make_tmap_4d(&mapX, dtype, p.x, dims, str, box, 0);
+        if (rc != VMB_OK) return rc;
+    }
+    auto kern = conv3x3_tma_kernel<T, MT, STAGES, NHWC>;
+    static bool attr_set = false;  // idempotent: a race only repeats the call
+    if (!attr_set) {
+        VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr_set = true;
+    }
+    const dim3 grid(cdiv(p.W, kTW) * cdiv(p.H, kTH), cdiv(p.Cout, MT), p.B);
+    VMB_CUDA(launch_pdl(kern, grid, dim3(128), SMEM, stream, p, mapW, mapX));
+    return VMB_OK;
+}
+
+template <typename T>
+int launch_16(const Conv3Params& p, int dtype, cudaStream_t stream) {
+    const int tiles = cdiv(p.W, kTW) * cdiv(p.H, kTH) * p.B;
+    if (p.in_nhwc) {  // dense (B,H,W,Cin), Cin % 8 == 0, 16 B-aligned base (checked by the C-ABI entry)
+        if (p.Cout <= 16) return launch_tma<T, 16, 4, true>(p, dtype, stream);
+        return launch_tma<T, 64, 3, true>(p, dtype, stream);
+    }
+    const bool aligned = p.W % 8 == 0 && p.x_bs % 8 == 0 && p.x_cs % 8 == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 &&
+                         p.x_cs >= (int64_t)p.H * p.W && p.x_bs > 0;
+    if (!aligned) return p.Cout <= 16 ? launch_generic<T, 16>(p, stream) : launch_generic<T, 64>(p, stream);
+    // output-channel tile: the widest one that still gives about two CTAs per SM (these problems are latency-bound: parallelism
+    // first, operand reuse second)
+    const int want = 2 * 148;
+    if (p.Cout > 32 && tiles * cdiv(p.Cout, 64) >= want) return launch_tma<T, 64, 3, false>(p, dtype, stream);
+    if (p.Cout > 16 && tiles * cdiv(p.Cout, 32) >= want) return launch_tma<T, 32, 3, false>(p, dtype, stream);
+    return launch_tma<T, 16, 4, false>(p, dtype, stream);
 }
 
 }  // namespace
 
 int conv3x3_launch(const Conv3Params& p, int dtype, cudaStream_t stream) {
-    if (dtype == VMB_BF16) return launch_16<__nv_bfloat16>(p, stream);
-    if (dtype == VMB_F16) return launch_16<__half>(p, stream);
+    if (dtype == VMB_BF16) return launch_16<__nv_bfloat16>(p, dtype, stream);
+    if (dtype == VMB_F16) return launch_16<__half>(p, dtype, stream);
     const dim3 grid(cdiv(p.W, kTW) * cdiv(p.H, kTH), cdiv(p.Cout, 16), p.B);
     if (p.in_nhwc) {
         VMB_CUDA(launch_pdl(conv3x3_simt_kernel<float, true>, grid, dim3(128), 0, stream, p));

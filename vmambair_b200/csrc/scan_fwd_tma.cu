@@ -352,7 +352,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 int make_tmap_4d(CUtensorMap* map, int dtype, const void* base, const uint64_t dims[4], const int64_t strides_elts[3],
-                 const uint32_t box[4]) {
+                 const uint32_t box[4], int swizzle) {
     EncodeTiledFn fn = encode_fn();
     VMB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the CUDA driver");
     CUtensorMapDataType t;
@@ -372,8 +372,10 @@ int make_tmap_4d(CUtensorMap* map, int dtype, const void* base, const uint64_t d
         gstr[i] = s;
         dense = s * dims[i + 1];
     }
+    const CUtensorMapSwizzle sw = swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle == 3 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
     const CUresult r = fn(map, t, 4, const_cast<void*>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VMB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return VMB_OK;
 }

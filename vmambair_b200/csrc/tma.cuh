@@ -57,7 +57,8 @@ inline int dtype_to_tmap(int dtype, CUtensorMapDataType* out) {
 
 // 4-D tensor (d0 contiguous).  stride_k = element stride of dimension k (k = 1..3), box_k = box extent.  Dimensions of extent 1 may
 // carry any stride.  Requires a 16 B-aligned base and byte strides that are multiples of 16 (the caller checked: vec_ok).
+// swizzle: 0 none, 1 / 2 / 3 = CU_TENSOR_MAP_SWIZZLE_32B / 64B / 128B (the box's innermost extent must span at most that many bytes).
 int make_tmap_4d(CUtensorMap* map, int dtype, const void* base, const uint64_t dims[4], const int64_t strides_elts[3],
-                 const uint32_t box[4]);
+                 const uint32_t box[4], int swizzle = 0);
 
 }  // namespace vmb
