@@ -197,11 +197,7 @@ extern "C" int vmb_conv3x3(const vmb_conv3x3_args* a, void* stream) {
     VMB_CHECK((cdiv(a->Cout, 16)) <= 65535, "conv3x3: too many output channels");
     Conv3Params p{a->x, a->w, a->bias, a->out, a->add, a->batch, a->Cin, a->Cout, a->H, a->W, a->in_nhwc, a->mode, a->add_scale,
                   (a->Cout + 63) / 64 * 64, (a->Cin + 15) / 16 * 16,
-                  a->in_nhwc ? (int64_t)a->H * a->W * a->Cin : a->x_bs, a->x_cs, a->o_bs, a->o_cs, a->add_bs, a->add_cs, 0};
-    {
-        static const int dbg = [] { const char* e = getenv("VMB_CONV_DBG"); return e ? atoi(e) : 0; }();
-        p.dbg = dbg;
-    }
+                  a->in_nhwc ? (int64_t)a->H * a->W * a->Cin : a->x_bs, a->x_cs, a->o_bs, a->o_cs, a->add_bs, a->add_cs};
     return conv3x3_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
 }
 

@@ -45,8 +45,7 @@ template <> __device__ __forceinline__ void mma16816<__half>(float (&c)[4], cons
 
 // One output element (b, m, y, x) of the convolution -> its place in `out` (see vmb_conv3x3_args.mode).
 template <typename T>
-__device__ __forceinline__ void conv_store(const Conv3Params& p, int b, int m, int y, int x, float v) {
-    if (p.bias) v += p.bias[m];
+__device__ __forceinline__ void conv_store_raw(const Conv3Params& p, int b, int m, int y, int x, float v) {
     T* out = static_cast<T*>(p.out) + (int64_t)b * p.o_bs;
     if (p.mode == VMB_CONV_PLAIN) {
         out[(int64_t)m * p.o_cs + (int64_t)y * p.W + x] = from_f32<T>(v);
@@ -60,6 +59,57 @@ __device__ __forceinline__ void conv_store(const Conv3Params& p, int b, int m, i
         v += to_f32<T>(add[(int64_t)(y / p.add_scale) * (p.W / p.add_scale) + x / p.add_scale]);
         out[(int64_t)m * p.o_cs + (int64_t)y * p.W + x] = from_f32<T>(v);
     }
+}
+
+// Fragment store of the tensor-core kernels: this lane holds channel m at (y, x) and (y, x + 1), x even.  Called by all 32 lanes
+// (the shuffle modes trade one element with a neighbour lane so that every lane writes one 32-bit word):
+//   PLAIN / ADD_NEAREST  (x, x+1) of channel m are adjacent in the output;
+//   SHUFFLE2             channels (m even, m+1) at x are adjacent (columns 2x, 2x+1): partner = lane ^ 4 (row g ^ 1);
+//   UNSHUFFLE2           x and x+2 of one parity are adjacent (columns x/2, x/2+1 of channel 4m+2(y%2)+x%2): partner = lane ^ 1.
+// pair_ok: the 32-bit stores are aligned (even strides / base, W % 4 == 0); otherwise element-wise stores.
+template <typename T>
+__device__ __forceinline__ void conv_store_frag(const Conv3Params& p, int b, int m, int y, int x, float v0, float v1, bool pair_ok,
+                                                int lane) {
+    const bool valid = m < p.Cout && y < p.H && x < p.W;
+    const float bs = (p.bias && m < p.Cout) ? p.bias[m] : 0.f;
+    v0 += bs;
+    v1 += bs;
+    T* out = static_cast<T*>(p.out) + (int64_t)b * p.o_bs;
+    if (!pair_ok) {
+        if (valid) {
+            conv_store_raw<T>(p, b, m, y, x, v0);
+            if (x + 1 < p.W) conv_store_raw<T>(p, b, m, y, x + 1, v1);
+        }
+        return;
+    }
+    if (p.mode == VMB_CONV_SHUFFLE2) {
+        const float s0 = __shfl_xor_sync(0xffffffffu, v0, 4), s1 = __shfl_xor_sync(0xffffffffu, v1, 4);
+        if (valid) {
+            const bool odd = (lane >> 2) & 1;  // m odd
+            T* o = out + (int64_t)(m >> 2) * p.o_cs + (int64_t)(2 * y + ((m >> 1) & 1)) * (2 * p.W) + 2 * x + (odd ? 2 : 0);
+            *reinterpret_cast<uint32_t*>(o) = odd ? pack2<T>(s1, v1) : pack2<T>(v0, s0);
+        }
+    } else if (p.mode == VMB_CONV_UNSHUFFLE2) {
+        const float s0 = __shfl_xor_sync(0xffffffffu, v0, 1), s1 = __shfl_xor_sync(0xffffffffu, v1, 1);
+        if (valid) {
+            const bool odd = lane & 1;  // x / 2 odd
+            T* o = out + (int64_t)(4 * m + 2 * (y & 1) + (odd ? 1 : 0)) * p.o_cs + (int64_t)(y >> 1) * (p.W >> 1) + (x >> 1) - (odd ? 1 : 0);
+            *reinterpret_cast<uint32_t*>(o) = odd ? pack2<T>(s1, v1) : pack2<T>(v0, s0);
+        }
+    } else if (valid) {
+        if (p.mode == VMB_CONV_ADD_NEAREST) {
+            const T* add = static_cast<const T*>(p.add) + (int64_t)b * p.add_bs + (int64_t)m * p.add_cs +
+                           (int64_t)(y / p.add_scale) * (p.W / p.add_scale);
+            v0 += to_f32<T>(add[x / p.add_scale]);
+            v1 += to_f32<T>(add[(x + 1) / p.add_scale]);
+        }
+        *reinterpret_cast<uint32_t*>(out + (int64_t)m * p.o_cs + (int64_t)y * p.W + x) = pack2<T>(v0, v1);
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void conv_store(const Conv3Params& p, int b, int m, int y, int x, float v) {
+    conv_store_raw<T>(p, b, m, y, x, p.bias ? v + p.bias[m] : v);
 }
 
 // ---- 16-bit I/O, any NCHW geometry (ragged W, unaligned views): implicit GEMM on mma.sync ------------------------------------
@@ -239,29 +289,32 @@ __global__ void __launch_bounds__(128) conv3x3_tma_kernel(const Conv3Params p, c
     const int nchunk = (p.Cin + 15) / 16;
 
     if (tid == 0) {
-        if (p.dbg & 1) {
-            tma_prefetch_desc(&mapW);
-            tma_prefetch_desc(&mapX);
-        }
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) mbarrier_init(&full[s], 1);
         mbarrier_init_fence();
     }
     __syncthreads();
-    pdl_wait();  // the activations are the preceding kernel's output
-    auto issue = [&](int kc, int s) {
-        unsigned char* A = smem + s * Cfg::STAGE;
-        mbarrier_expect_tx(&full[s], ((p.dbg & 4) ? 0 : Cfg::A_BYTES) + ((p.dbg & 8) ? 0 : Cfg::B_BYTES));
-        if (!(p.dbg & 4)) tma_load_4d(A, &mapW, &full[s], kc * 16, m0, 0, 0);
-        if (!(p.dbg & 8)) {
-            if constexpr (NHWC) tma_load_4d(A + Cfg::A_BYTES, &mapX, &full[s], kc * 16, x0 - 1, y0 - 1, b);
-            else tma_load_4d(A + Cfg::A_BYTES, &mapX, &full[s], x0 - kRawX, y0 - 1, kc * 16, b);
-        }
+    // one stage = the weights box + the input box on one mbarrier; the weights are static parameters, so the boxes of the first
+    // STAGES chunks are requested while the preceding kernel of the stream is still draining (PDL), the activations after it
+    auto issue_w = [&](int kc, int s) {
+        mbarrier_expect_tx(&full[s], Cfg::A_BYTES + Cfg::B_BYTES);
+        tma_load_4d(smem + s * Cfg::STAGE, &mapW, &full[s], kc * 16, m0, 0, 0);
+    };
+    auto issue_x = [&](int kc, int s) {
+        unsigned char* dst = smem + s * Cfg::STAGE + Cfg::A_BYTES;
+        if constexpr (NHWC) tma_load_4d(dst, &mapX, &full[s], kc * 16, x0 - 1, y0 - 1, b);
+        else tma_load_4d(dst, &mapX, &full[s], x0 - kRawX, y0 - 1, kc * 16, b);
     };
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s)
-            if (s < nchunk) issue(s, s);
+            if (s < nchunk) issue_w(s, s);
+    }
+    pdl_wait();
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+            if (s < nchunk) issue_x(s, s);
     }
 
     float acc[MI][4][4];
@@ -282,6 +335,20 @@ __global__ void __launch_bounds__(128) conv3x3_tma_kernel(const Conv3Params p, c
     bool jok[4];  // n-tiles inside the image (warp-uniform): the others are skipped
 #pragma unroll
     for (int j = 0; j < 4; ++j) jok[j] = (y0 + trow0 + (j >> 1) < p.H) && (x0 + (j & 1) * 8 < p.W);
+    // re-layout work list of this thread (NCHW): item i = tid + 128 j -> (halo pixel, channel pair); source offset in the raw box
+    // (low half) and destination offset in the [pixel][channel] tile (high half), fixed for the whole K loop
+    constexpr int NT = (8 * kHalo + 127) / 128;
+    uint32_t toff[NHWC ? 1 : NT];
+    if constexpr (!NHWC) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int i = tid + 128 * j;
+            const int hp = i % kHalo, cp = i / kHalo;
+            const uint32_t src = 2 * cp * kRawPlane + (hp / kHaloW) * (kRawW * 2) + (hp % kHaloW + kRawX - 1) * 2;
+            const uint32_t dst = hp * kBtPitch + cp * 4;
+            toff[j] = cp < 8 ? (src | (dst << 16)) : 0xffffffffu;
+        }
+    }
 
     for (int kc = 0; kc < nchunk; ++kc) {
         const int slot = kc % STAGES;
@@ -290,17 +357,17 @@ __global__ void __launch_bounds__(128) conv3x3_tma_kernel(const Conv3Params p, c
         const unsigned char* Braw = A + Cfg::A_BYTES;
         if constexpr (!NHWC) {
             // [16 planes][10][32] -> [180 pixels][16 channels]: two channels of one pixel per packed 32-bit store
+            uint32_t tv[NT];
 #pragma unroll
-            for (int j = 0; j < (8 * kHalo + 127) / 128; ++j) {
-                const int i = tid + 128 * j;
-                const int hp = i % kHalo, cp = i / kHalo;
-                if (cp < 8) {
-                    const unsigned char* src = Braw + 2 * cp * kRawPlane + (hp / kHaloW) * (kRawW * 2) + (hp % kHaloW + kRawX - 1) * 2;
-                    const uint32_t v = *reinterpret_cast<const unsigned short*>(src) |
-                                       (uint32_t(*reinterpret_cast<const unsigned short*>(src + kRawPlane)) << 16);
-                    *reinterpret_cast<uint32_t*>(Bt + hp * kBtPitch + cp * 4) = v;
-                }
+            for (int j = 0; j < NT; ++j) {
+                const unsigned char* src = Braw + (toff[j] & 0xffffu);
+                tv[j] = toff[j] != 0xffffffffu ? (*reinterpret_cast<const unsigned short*>(src) |
+                                                  (uint32_t(*reinterpret_cast<const unsigned short*>(src + kRawPlane)) << 16))
+                                               : 0u;
             }
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+                if (toff[j] != 0xffffffffu) *reinterpret_cast<uint32_t*>(Bt + (toff[j] >> 16)) = tv[j];
             __syncthreads();
         }
 #pragma unroll
@@ -328,20 +395,21 @@ __global__ void __launch_bounds__(128) conv3x3_tma_kernel(const Conv3Params p, c
         __syncthreads();  // every warp is done with this stage (and with Bt)
         if (tid == 0 && kc + STAGES < nchunk) {
             fence_proxy_async();  // the stage was read through the generic proxy; the refill writes through the async proxy
-            issue(kc + STAGES, slot);
+            issue_w(kc + STAGES, slot);
+            issue_x(kc + STAGES, slot);
         }
     }
 
+    // 32-bit stores need even element offsets: W % 4 == 0 (true on this path), even strides, 4 B-aligned base
+    const bool pair_ok = p.W % 4 == 0 && p.o_bs % 2 == 0 && p.o_cs % 2 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 3) == 0;
 #pragma unroll
     for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int m = m0 + mi * 16 + g + (e >> 1) * 8;
-                const int y = y0 + trow0 + (j >> 1), x = x0 + (j & 1) * 8 + 2 * t + (e & 1);
-                if (m < p.Cout && y < p.H && x < p.W) conv_store<T>(p, b, m, y, x, acc[mi][j][e]);
-            }
+            for (int h = 0; h < 2; ++h)
+                conv_store_frag<T>(p, b, m0 + mi * 16 + g + h * 8, y0 + trow0 + (j >> 1), x0 + (j & 1) * 8 + 2 * t, acc[mi][j][2 * h],
+                                   acc[mi][j][2 * h + 1], pair_ok, lane);
 }
 
 // ---- fp32 I/O (parity mode): direct FFMA convolution, one output pixel x 16 output channels per thread ---------------------
@@ -418,14 +486,14 @@ int launch_tma(const Conv3Params& p, int dtype, cudaStream_t stream) {
         const uint64_t dims[4] = {(uint64_t)p.Kpad, (uint64_t)p.Mpad, 9, 1};
         const int64_t str[3] = {p.Kpad, (int64_t)p.Mpad * p.Kpad, (int64_t)9 * p.Mpad * p.Kpad};
         const uint32_t box[4] = {16, (uint32_t)MT, 9, 1};
-        const int rc = make_tmap_4d(&mapW, dtype, p.w, dims, str, box, (p.dbg & 2) ? 0 : 1);
+        const int rc = make_tmap_4d(&mapW, dtype, p.w, dims, str, box, 1);
         if (rc != VMB_OK) return rc;
     }
     if (NHWC) {
         const uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
         const int64_t str[3] = {p.Cin, (int64_t)p.W * p.Cin, (int64_t)p.H * p.W * p.Cin};
         const uint32_t box[4] = {16, (uint32_t)kHaloW, (uint32_t)(kTH + 2), 1};
-        const int rc = make_tmap_4d(&mapX, dtype, p.x, dims, str, box, (p.dbg & 2) ? 0 : 1);
+        const int rc = make_tmap_4d(&mapX, dtype, p.x, dims, str, box, 1);
         if (rc != VMB_OK) return rc;
     } else {
         const uint64_t dims[4] = {(uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.Cin, (uint64_t)p.B};
@@ -455,9 +523,9 @@ int launch_16(const Conv3Params& p, int dtype, cudaStream_t stream) {
     const bool aligned = p.W % 8 == 0 && p.x_bs % 8 == 0 && p.x_cs % 8 == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 &&
                          p.x_cs >= (int64_t)p.H * p.W && p.x_bs > 0;
     if (!aligned) return p.Cout <= 16 ? launch_generic<T, 16>(p, stream) : launch_generic<T, 64>(p, stream);
-    // output-channel tile: the widest one that still gives about two CTAs per SM (these problems are latency-bound: parallelism
-    // first, operand reuse second)
-    const int want = 2 * 148;
+    // output-channel tile: the widest one that still fills one wave of CTAs (every K chunk costs a CTA a fixed barrier / re-layout
+    // overhead that a wider tile amortises, but an idle SM amortises nothing)
+    const int want = 148;
     if (p.Cout > 32 && tiles * cdiv(p.Cout, 64) >= want) return launch_tma<T, 64, 3, false>(p, dtype, stream);
     if (p.Cout > 16 && tiles * cdiv(p.Cout, 32) >= want) return launch_tma<T, 32, 3, false>(p, dtype, stream);
     return launch_tma<T, 16, 4, false>(p, dtype, stream);

@@ -54,7 +54,6 @@ struct Conv3Params {
     int in_nhwc, mode, add_scale;
     int Mpad, Kpad;  // packed weights: [9 taps][Mpad][Kpad], Mpad % 64 == 0, Kpad % 16 == 0, zero padded
     int64_t x_bs, x_cs, o_bs, o_cs, add_bs, add_cs;
-    int dbg;  // VMB_CONV_DBG (bring-up knob of the TMA path)
 };
 int conv3x3_launch(const Conv3Params& p, int dtype, cudaStream_t stream);
 int pixlin_launch(const PixlinParams& p, int dtype, int out_dtype, cudaStream_t stream);
