@@ -145,6 +145,10 @@ typedef struct {
     int64_t out_ks; /* element stride between the four directions of `out` (0: rows * H * W, dense) */
 } vmb_cross_scan_args;
 int vmb_cross_scan(const vmb_cross_scan_args* a, void* stream);
+/* 1..4 cross-scans of one geometry (same dtype, batch, H, W; own sources, row counts and destinations) in ONE launch: what the
+ * training path needs per block -- x, delta and B|C gathered into the four scan orders (forward), du, ddelta, dB, dC scattered back
+ * (backward; the inverse orders = H and W swapped).  Same values as nseg calls of vmb_cross_scan. */
+int vmb_cross_scan_multi(const vmb_cross_scan_args* segs, int nseg, void* stream);
 
 /* (B*C) planes of H x W -> W x H (the transposed copy of x that directions 1 and 3 scan). */
 typedef struct { const void* x; void* out; int planes, H, W; int dtype; } vmb_transpose_args;

@@ -66,3 +66,20 @@ def test_shard_batch_covers_everything():
                 lo, hi = shard_batch(gb, r, w)
                 seen += list(range(lo, hi))
             assert seen == list(range(gb))
+
+
+def test_flat_allreduce_mixed_dtype_and_missing_grads():
+    """a parameter whose dtype differs from the flat buffer keeps its own .grad (copied in at reduce time); a parameter without a
+    gradient this step contributes zeros instead of the previous step's values (single process: no collective needed)"""
+    a = torch.nn.Parameter(torch.ones(3))
+    b = torch.nn.Parameter(torch.ones(2, dtype=torch.float64))
+    c = torch.nn.Parameter(torch.ones(4))
+    gar = FlatGradAllReduce([a, b, c]).attach()
+    assert a.grad is gar.views[0] and b.grad is None
+    (a.sum() * 2 + b.sum() * 3 + c.sum() * 5).backward()
+    gar.reduce(1)
+    assert gar.flat.tolist() == [2.0] * 3 + [3.0] * 2 + [5.0] * 4
+    assert b.grad.dtype == torch.float64  # untouched: assigning the fp32 view would raise
+    c.grad = None
+    gar.reduce(1)
+    assert gar.flat[5:].tolist() == [0.0] * 4 and gar.flat[:3].tolist() == [2.0] * 3

@@ -341,3 +341,33 @@ def test_dwconv_row_block_kernel_bit_identical(dtype, H, W, monkeypatch):
                    ops.dwconv3x3(xin, w, b, C, H, W, 1), ops.dwconv3x3(xin, w, None, C, H, W, 1))
     for a, r in zip(outs["2"], outs["1"]):
         assert torch.equal(a, r)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("hw", [(64, 64), (32, 48), (10, 12)])
+def test_cross_scan_multi_equals_separate_launches(hw, dtype):
+    """vmb_cross_scan_multi (one launch for the x / delta / B|C gathers of a block, one for the du / ddelta / dB / dC scatters of its
+    backward) against one vmb_cross_scan per segment: a permutation, so bit-exact; (10, 12) takes the per-segment fallback"""
+    from vmambair_b200 import ops
+    H, W = hw
+    B, C, N, L = 2, 24, 16, H * W
+    torch.manual_seed(0)
+    xc = torch.randn(B, C, L, device="cuda").to(dtype)
+    dbl4 = torch.randn(B, 4, C + 2 * N, L, device="cuda").to(dtype)
+    segs = [([xc] * 4, C), ([dbl4[:, k, :C] for k in range(4)], C), ([dbl4[:, k, C:] for k in range(4)], 2 * N)]
+    got = ops.cross_scan_multi([(s, r, None) for s, r in segs], H, W)
+    for (s, r), g in zip(segs, got):
+        assert torch.equal(g, ops.cross_scan(s, r, H, W))
+    # scatter direction: four segments, three of them into slices of one tensor, H and W swapped
+    du, dd = torch.randn(B, 4 * C, L, device="cuda").to(dtype), torch.randn(B, 4 * C, L, device="cuda").to(dtype)
+    dB, dC = torch.randn(B, 4, N, L, device="cuda").to(dtype), torch.randn(B, 4, N, L, device="cuda").to(dtype)
+    wide = torch.zeros(B, 4, C + 2 * N, L, device="cuda", dtype=dtype)
+    ref = torch.zeros_like(wide)
+    back = [([du.view(B, 4, C, L)[:, k] for k in range(4)], C, None), ([dd.view(B, 4, C, L)[:, k] for k in range(4)], C, wide[:, :, :C]),
+            ([dB[:, k] for k in range(4)], N, wide[:, :, C:C + N]), ([dC[:, k] for k in range(4)], N, wide[:, :, C + N:])]
+    g0 = ops.cross_scan_multi(back, W, H)[0]
+    assert torch.equal(g0, ops.cross_scan(back[0][0], C, W, H))
+    ops.cross_scan(back[1][0], C, W, H, out=ref[:, :, :C])
+    ops.cross_scan(back[2][0], N, W, H, out=ref[:, :, C:C + N])
+    ops.cross_scan(back[3][0], N, W, H, out=ref[:, :, C + N:])
+    assert torch.equal(wide, ref)

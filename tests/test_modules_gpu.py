@@ -134,3 +134,28 @@ def test_unmodified_call_pattern_selective_scan_cuda_core():
     assert out.shape == u.shape and x.dtype == torch.float32
     g = core.bwd(u, dl, A, Bm, Cm, D, bias, torch.randn_like(out), x, True, 1)
     assert len(g) == 7 and g[0].shape == u.shape and g[2].shape == A.shape and g[3].shape == Bm.shape
+
+
+def test_wide_net_dim64_falls_back_per_block_and_runs():
+    """MambaSISR6(dim=64) has a C = 512 latent level, beyond the fused kernels' K <= 384 LayerNorm prologue: that level
+    takes the composed path (with a warning), the others the fused kernels, and the result equals the all-composed forward."""
+    import warnings
+    torch.manual_seed(4)
+    net = archs.MambaSISR6(dim=64, num_blocks=[1, 1, 1, 1], num_refinement_blocks=1).to("cuda").eval()
+    x = torch.rand(1, 3, 32, 32, device="cuda")
+    with torch.no_grad(), warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        y = net(x)
+        assert any("fused OSS block not available" in str(i.message) for i in w)
+        from vmambair_b200 import unet
+        unet.set_mode("torch")
+        try:
+            blocks = [m for m in net.modules() if isinstance(m, archs.MamberBlock)]
+            fwd = archs.MamberBlock.forward
+            archs.MamberBlock.forward = lambda self, t, out=None: self.forward_compose(t)
+            ref = net(x)
+        finally:
+            archs.MamberBlock.forward = fwd
+            unet.set_mode("native")
+    assert len(blocks) == 9 and torch.isfinite(y).all()
+    torch.testing.assert_close(y, ref, rtol=2e-3, atol=2e-4)

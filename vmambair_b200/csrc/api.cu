@@ -149,6 +149,26 @@ extern "C" int vmb_cross_scan(const vmb_cross_scan_args* a, void* stream) {
     return cross_scan_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int vmb_cross_scan_multi(const vmb_cross_scan_args* segs, int nseg, void* stream) {
+    VMB_CHECK(segs && nseg >= 1 && nseg <= 4, "cross_scan_multi: 1..4 segments");
+    CrossScanMulti m{};
+    m.nseg = nseg;
+    int rows = 0;
+    for (int i = 0; i < nseg; ++i) {
+        const vmb_cross_scan_args* a = segs + i;
+        VMB_CHECK(a->src[0] && a->src[1] && a->src[2] && a->src[3] && a->out, "cross_scan_multi: null pointer (segment %d)", i);
+        VMB_CHECK(a->dtype == segs[0].dtype && a->batch == segs[0].batch && a->H == segs[0].H && a->W == segs[0].W,
+                  "cross_scan_multi: the segments must share dtype, batch, H and W");
+        VMB_CHECK(a->rows > 0, "cross_scan_multi: empty segment %d", i);
+        m.seg[i] = CrossScanParams{{a->src[0], a->src[1], a->src[2], a->src[3]}, a->out, a->batch, a->rows, a->H, a->W, a->src_bs,
+                                   a->src_rs, a->out_bs, a->out_ks > 0 ? a->out_ks : (int64_t)a->rows * a->H * a->W};
+        rows += a->rows;
+        m.row_end[i] = rows;
+    }
+    VMB_CHECK(dt_ok(segs[0].dtype), "cross_scan_multi: bad dtype");
+    return cross_scan_multi_launch(m, segs[0].dtype, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int64_t vmb_merge_workspace_bytes(int batch, int C, int H, int W) {
     // fp32 merged values + per-pixel (sum, sum of squares) + per-tile channel sums + per-image tile counters of the single-kernel path
     const int64_t tiles = (int64_t)((H + 15) / 16) * ((W + 15) / 16);

@@ -258,15 +258,11 @@ __global__ void __launch_bounds__(256) cross_scan_kernel(const CrossScanParams p
 // in-register for k = 2), 8 consecutive h gathered from the fp32 smem tile for the column-major orders.  8x fewer load / store
 // instructions than the per-element kernel above (which stays as the fallback for odd geometries).
 template <typename in_t>
-__global__ void __launch_bounds__(256) cross_scan_vec_kernel(const CrossScanParams p) {
-    pdl_trigger();
-    pdl_wait();
+__device__ __forceinline__ void cross_scan_vec_body(const CrossScanParams& p, const int row, const int b, float* cs_tile) {
     constexpr int V = Vec<in_t>::N;           // 8 (16-bit) or 4 (fp32) elements per 16 B
     constexpr int TS = 64;
-    extern __shared__ float cs_tile[];        // [nsrc][TS][TS + 1]
     const int tiles_w = (p.W + TS - 1) / TS;
     const int h0 = (blockIdx.x / tiles_w) * TS, w0 = (blockIdx.x % tiles_w) * TS;
-    const int row = blockIdx.y, b = blockIdx.z;
     const int L = p.H * p.W;
     const bool same = p.src[0] == p.src[1] && p.src[0] == p.src[2] && p.src[0] == p.src[3];
     const int nsrc = same ? 1 : 4;
@@ -324,6 +320,70 @@ __global__ void __launch_bounds__(256) cross_scan_vec_kernel(const CrossScanPara
             }
         }
     }
+}
+
+template <typename in_t>
+__global__ void __launch_bounds__(256) cross_scan_vec_kernel(const CrossScanParams p) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ float cs_tile[];        // [nsrc][64][65]
+    cross_scan_vec_body<in_t>(p, blockIdx.y, blockIdx.z, cs_tile);
+}
+
+// Up to four cross-scans of one geometry in ONE launch (the training path gathers x, delta and B|C of a block into the four scan
+// orders, and scatters du, ddelta, dB, dC back: 3 + 4 launches of 5-13 us each for a few MB -- launch / latency bound): blockIdx.y
+// walks the rows of all segments.
+template <typename in_t>
+__global__ void __launch_bounds__(256) cross_scan_vec_multi_kernel(const CrossScanMulti m) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ float cs_tile[];
+    int row = blockIdx.y, s = 0;
+    while (s + 1 < m.nseg && row >= m.row_end[s]) ++s;
+    if (s > 0) row -= m.row_end[s - 1];
+    cross_scan_vec_body<in_t>(m.seg[s], row, blockIdx.z, cs_tile);
+}
+
+static bool cross_scan_vec_ok(const CrossScanParams& p, int dtype) {
+    const int v = dtype == VMB_F32 ? 4 : 8;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    return p.H % v == 0 && p.W % v == 0 && al16(p.src[0]) && al16(p.src[1]) && al16(p.src[2]) && al16(p.src[3]) && al16(p.out) &&
+           p.src_bs % v == 0 && p.src_rs % v == 0 && p.out_bs % v == 0 && p.out_ks % v == 0;
+}
+
+int cross_scan_multi_launch(const CrossScanMulti& m, int dtype, cudaStream_t stream) {
+    bool vec = true, all_same = true;
+    for (int i = 0; i < m.nseg; ++i) {
+        const CrossScanParams& p = m.seg[i];
+        vec = vec && cross_scan_vec_ok(p, dtype) && p.B == m.seg[0].B && p.H == m.seg[0].H && p.W == m.seg[0].W;
+        all_same = all_same && p.src[0] == p.src[1] && p.src[0] == p.src[2] && p.src[0] == p.src[3];
+    }
+    const char* ve = getenv("VMB_CROSS_SCAN_MULTI");
+    if (!vec || m.nseg == 1 || m.row_end[m.nseg - 1] > 65535 || (ve && atoi(ve) == 0)) {  // one launch per segment: same values
+        for (int i = 0; i < m.nseg; ++i) {
+            const int rc = cross_scan_launch(m.seg[i], dtype, stream);
+            if (rc != VMB_OK) return rc;
+        }
+        return VMB_OK;
+    }
+    const CrossScanParams& p0 = m.seg[0];
+    const size_t smem = sizeof(float) * (all_same ? 1 : 4) * 64 * 65;
+    const dim3 grid(((p0.H + 63) / 64) * ((p0.W + 63) / 64), m.row_end[m.nseg - 1], p0.B);
+#define VMB_CSM(T)                                                                                                              \
+    {                                                                                                                           \
+        if (smem > 48 * 1024)                                                                                                   \
+            VMB_CUDA(cudaFuncSetAttribute(cross_scan_vec_multi_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        VMB_CUDA(launch_pdl(cross_scan_vec_multi_kernel<T>, grid, dim3(256), smem, stream, m));                                  \
+    }
+    switch (dtype) {
+        case VMB_F32: VMB_CSM(float) break;
+        case VMB_BF16: VMB_CSM(__nv_bfloat16) break;
+        case VMB_F16: VMB_CSM(__half) break;
+        default: set_error("cross_scan: unsupported dtype %d", dtype); return VMB_ERR_INVALID;
+    }
+#undef VMB_CSM
+    VMB_CUDA(cudaGetLastError());
+    return VMB_OK;
 }
 
 int cross_scan_launch(const CrossScanParams& p, int dtype, cudaStream_t stream) {

@@ -24,6 +24,11 @@ struct CrossScanParams {
     int B, rows, H, W;
     int64_t src_bs, src_rs, out_bs, out_ks;
 };
+struct CrossScanMulti {
+    int nseg;
+    int row_end[4];  // cumulative row counts of the segments
+    CrossScanParams seg[4];
+};
 struct MergeParams {
     const void* ys; const void* z; const float* ln_w; const float* ln_b; void* y2; float* pooled;
     int B, C, H, W;
@@ -61,6 +66,7 @@ bool pixlin_tc_applicable(const PixlinParams& p, int dtype, int out_dtype);
 int pixlin_tc_launch(const PixlinParams& p, int dtype, cudaStream_t stream);
 int dwconv_launch(const DwParams& p, int dtype, cudaStream_t stream);
 int cross_scan_launch(const CrossScanParams& p, int dtype, cudaStream_t stream);
+int cross_scan_multi_launch(const CrossScanMulti& m, int dtype, cudaStream_t stream);
 int merge_launch(const MergeParams& p, int dtype, cudaStream_t stream);
 int transpose_launch(const TransposeParams& p, int dtype, cudaStream_t stream);
 int pixel_shuffle_launch(const PixelShuffleParams& p, int dtype, cudaStream_t stream);

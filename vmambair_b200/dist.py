@@ -36,11 +36,16 @@ class FlatGradAllReduce:
         return self
 
     def reduce(self, world: int, group=None):
+        """gathers whatever is not already a view (a parameter whose dtype differs from the flat buffer keeps its own .grad and is
+        copied in; a parameter that received no gradient this step contributes zeros, not last step's values), then one all-reduce"""
         if any(p.grad is not v for p, v in zip(self.params, self.views)):
             for p, v in zip(self.params, self.views):
-                if p.grad is not None and p.grad is not v:
+                if p.grad is None:
+                    v.zero_()
+                elif p.grad is not v:
                     v.copy_(p.grad)
-                    p.grad = v
+                    if v.dtype == p.dtype:
+                        p.grad = v
         if world > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             self.flat.div_(world)

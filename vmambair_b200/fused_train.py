@@ -174,9 +174,8 @@ class _Front(torch.autograd.Function):
             cw9 = _f32(cw.view(C, 9))
             xc = ops.dwconv3x3(xz[:, :C], cw9, _f32(cb), C, H, W, 0)
             dbl4 = ops.pixlin(xc, Wbig).view(B, 4, C + 2 * N, L)   # delta, B, C of the four directions, pixel order
-            xs = ops.cross_scan([xc] * 4, C, H, W)
-            dts = ops.cross_scan([dbl4[:, k, :C] for k in range(4)], C, H, W)
-            bc = ops.cross_scan([dbl4[:, k, C:] for k in range(4)], 2 * N, H, W)
+            xs, dts, bc = ops.cross_scan_multi([([xc] * 4, C, None), ([dbl4[:, k, :C] for k in range(4)], C, None),
+                                                ([dbl4[:, k, C:] for k in range(4)], 2 * N, None)], H, W)  # one launch
             ys, ckpt = ops.selective_scan_fwd(xs.view(B, 4 * C, L), dts.view(B, 4 * C, L), A, bc[:, :, :N], bc[:, :, N:], _f32(Ds),
                                               _f32(dt_b.reshape(-1)), True, need_ckpt=True)
             y2, pooled, ws = ops.merge_norm_gate(ys.view(B, 4, C, L), xz[:, C:], _f32(on_w), _f32(on_b), C, H, W,
@@ -213,11 +212,11 @@ class _Front(torch.autograd.Function):
                 xs.view(B, 4 * C, L), dts.view(B, 4 * C, L), A, bc[:, :, :N], bc[:, :, N:], _f32(Ds), _f32(dt_b.reshape(-1)),
                 dys.view(B, 4 * C, L), ckpt, True, zeroed=(Z["dA"], g_dD, g_dbias))
             # back to pixel order: pi_k^-1 is pi_k with H and W swapped
-            dxc4 = ops.cross_scan([du.view(B, 4, C, L)[:, k] for k in range(4)], C, W, H)
             ddbl = torch.empty((B, 4, C + 2 * N, L), dtype=dt_, device=dev)
-            ops.cross_scan([ddelta.view(B, 4, C, L)[:, k] for k in range(4)], C, W, H, out=ddbl[:, :, :C])
-            ops.cross_scan([dB[:, k] for k in range(4)], N, W, H, out=ddbl[:, :, C:C + N])
-            ops.cross_scan([dC[:, k] for k in range(4)], N, W, H, out=ddbl[:, :, C + N:])
+            dxc4 = ops.cross_scan_multi([([du.view(B, 4, C, L)[:, k] for k in range(4)], C, None),
+                                         ([ddelta.view(B, 4, C, L)[:, k] for k in range(4)], C, ddbl[:, :, :C]),
+                                         ([dB[:, k] for k in range(4)], N, ddbl[:, :, C:C + N]),
+                                         ([dC[:, k] for k in range(4)], N, ddbl[:, :, C + N:])], W, H)[0]  # one launch
             ddbl = ddbl.view(B, Mb, L)
             dxc = ops.sum4_add(dxc4, ops.pixlin(ddbl, WbigT))  # x_proj data gradient + the four direction gradients of u
             xw, dtw = x_proj_w.detach(), dt_w.detach()

@@ -224,6 +224,29 @@ def pixel_shuffle2_nhwc(x):
     return out
 
 
+def cross_scan_multi(segs, H, W):
+    """segs: up to 4 tuples (srcs, rows, out|None) as for cross_scan, all of one geometry -> list of outputs, ONE launch."""
+    assert 1 <= len(segs) <= 4
+    arr = (_lib.CrossScanArgs * len(segs))()
+    outs = []
+    s00 = segs[0][0][0]
+    B = s00.shape[0]
+    for i, (srcs, rows, out) in enumerate(segs):
+        s0 = srcs[0]
+        if out is None:
+            out = torch.empty((B, 4, rows, H * W), dtype=s0.dtype, device=s0.device)
+        assert out.shape == (B, 4, rows, H * W) and out.stride(3) == 1 and out.stride(2) == H * W and out.dtype == s00.dtype
+        for t in srcs:
+            assert t.stride() == s0.stride() and t.stride(2) == 1 and t.dtype == s00.dtype and t.shape[0] == B
+        arr[i] = _lib.CrossScanArgs((C.c_void_p * 4)(*[t.data_ptr() for t in srcs]), _ptr(out), B, rows, H, W, s0.stride(0),
+                                    s0.stride(1), out.stride(0), _DT[s0.dtype], out.stride(1))
+        outs.append(out)
+    fn = _lib.lib().vmb_cross_scan_multi
+    with torch.cuda.device(s00.device), _timed("cross_scan", 0, s00.device, 1):
+        _lib.check(fn(arr, len(segs), _stream(s00)), "vmb_cross_scan_multi")
+    return outs
+
+
 CONV_PLAIN, CONV_UNSHUFFLE2, CONV_SHUFFLE2, CONV_ADD_NEAREST = 0, 1, 2, 3
 
 
