@@ -134,6 +134,10 @@ typedef struct {
     int dtype;
 } vmb_dwconv_args;
 int vmb_dwconv3x3(const vmb_dwconv_args* a, void* stream);
+/* mode 0 with a second output out_t (B, c_out, W*H) dense: every plane of `out` transposed -- the (W,H)-ordered copy of x that the
+ * column-major scan directions (cross_scan_2d :402) and their x_proj GEMM read; replaces a vmb_transpose_hw pass behind the conv
+ * (`out` must be dense). */
+int vmb_dwconv3x3_t(const vmb_dwconv_args* a, void* out_t, void* stream);
 
 /* four scan orders by index arithmetic (cross_scan_2d :401-404; CrossScan RealSR arch :325-343):
  * out[b][k][row][l] = src[k][b][row][pi_k(l)];  pi_0(l)=l, pi_1(w*H+h)=h*W+w, pi_2 = pi_0(L-1-l), pi_3 = pi_1(L-1-l). */

@@ -371,3 +371,20 @@ def test_cross_scan_multi_equals_separate_launches(hw, dtype):
     ops.cross_scan(back[2][0], N, W, H, out=ref[:, :, C:C + N])
     ops.cross_scan(back[3][0], N, W, H, out=ref[:, :, C + N:])
     assert torch.equal(wide, ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32, torch.float16])
+@pytest.mark.parametrize("geom", [(2, 24, 64, 64), (3, 10, 16, 8), (1, 7, 32, 48), (2, 5, 12, 20)])
+def test_dwconv_with_transposed_second_output(geom, dtype):
+    """vmb_dwconv3x3_t = vmb_dwconv3x3 (mode 0) + vmb_transpose_hw of its result, from one launch on the row-block path
+    ((32, 48) and (12, 20) take the per-pass fallback): bit-identical to the two-pass result"""
+    from vmambair_b200 import ops
+    B, C, H, W = geom
+    torch.manual_seed(7)
+    xz = torch.randn(B, 2 * C, H * W, device="cuda").to(dtype)
+    w9, b = torch.randn(C, 9, device="cuda"), torch.randn(C, device="cuda")
+    ref = ops.dwconv3x3(xz[:, :C], w9, b, C, H, W, 0)
+    out, out_t = ops.dwconv3x3_t(xz[:, :C], w9, b, C, H, W)
+    assert torch.equal(out, ref)
+    assert torch.equal(out_t, ops.transpose_hw(ref, H, W))
+    assert torch.equal(out_t.view(B, C, W, H), ref.view(B, C, H, W).transpose(2, 3))

@@ -190,6 +190,7 @@ SYMBOLS = {
     "vmb_pixel_shuffle2_nhwc": (C.c_int, [C.POINTER(PixelShuffleArgs), vp]),
     "vmb_conv3x3": (C.c_int, [C.POINTER(Conv3x3Args), vp]),
     "vmb_cross_scan_multi": (C.c_int, [C.POINTER(CrossScanArgs), C.c_int, vp]),
+    "vmb_dwconv3x3_t": (C.c_int, [C.POINTER(DwconvArgs), vp, vp]),
     "vmb_selective_scan_fwd_grouped": (C.c_int, [C.POINTER(ScanGroupedArgs), vp]),
     "vmb_channel_branch": (C.c_int, [C.POINTER(ChannelArgs), vp]),
     "vmb_layernorm_fwd": (C.c_int, [C.POINTER(LnFwdArgs), vp]),

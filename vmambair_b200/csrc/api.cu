@@ -135,9 +135,22 @@ extern "C" int vmb_dwconv3x3(const vmb_dwconv_args* a, void* stream) {
     VMB_CHECK(a && a->x && a->w && a->out, "dwconv: null pointer");
     VMB_CHECK(dt_ok(a->dtype), "dwconv: bad dtype");
     VMB_CHECK(a->batch > 0 && a->c_out > 0 && a->H > 0 && a->W > 0 && (long)a->batch * a->c_out <= 65535, "dwconv: bad sizes");
-    DwParams p{a->x, a->w, a->bias, a->out, a->batch, a->c_out, a->H, a->W, a->mode, a->x_bs, a->x_cs, a->o_bs, a->o_cs, false};
+    DwParams p{a->x, a->w, a->bias, a->out, a->batch, a->c_out, a->H, a->W, a->mode, a->x_bs, a->x_cs, a->o_bs, a->o_cs, false, nullptr};
     p.vec_ok = a->W % 8 == 0 && aligned16(a->x) && aligned16(a->out) && a->x_bs % 8 == 0 && a->x_cs % 8 == 0 &&
                a->o_bs % 8 == 0 && a->o_cs % 8 == 0;
+    return dwconv_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vmb_dwconv3x3_t(const vmb_dwconv_args* a, void* out_t, void* stream) {
+    VMB_CHECK(a && a->x && a->w && a->out && out_t, "dwconv_t: null pointer");
+    VMB_CHECK(dt_ok(a->dtype), "dwconv_t: bad dtype");
+    VMB_CHECK(a->mode == 0, "dwconv_t: the transposed second output exists for mode 0 (SiLU) only");
+    VMB_CHECK(a->batch > 0 && a->c_out > 0 && a->H > 0 && a->W > 0 && (long)a->batch * a->c_out <= 65535, "dwconv_t: bad sizes");
+    DwParams p{a->x, a->w, a->bias, a->out, a->batch, a->c_out, a->H, a->W, a->mode, a->x_bs, a->x_cs, a->o_bs, a->o_cs, false, out_t};
+    p.vec_ok = a->W % 8 == 0 && aligned16(a->x) && aligned16(a->out) && a->x_bs % 8 == 0 && a->x_cs % 8 == 0 &&
+               a->o_bs % 8 == 0 && a->o_cs % 8 == 0;
+    // 8 B / 16 B runs of four consecutive h in the (W, H) plane: H % 4 == 0 holds on the row-block path; the base must be aligned
+    if (!aligned16(out_t) || a->H % 4 != 0) p.vec_ok = false;
     return dwconv_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
 }
 

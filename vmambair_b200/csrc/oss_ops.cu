@@ -162,6 +162,23 @@ __global__ void __launch_bounds__(256) dwconv3x3_rows4_kernel(const DwParams p, 
     for (int o = 0; o < 4; ++o)
 #pragma unroll
         for (int j = 0; j < 8 / V; ++j) store_vec<in_t>(ob + (int64_t)(h0 + o) * p.W + w0 + j * V, a0[o] + j * V, V, true);
+    if (p.out_t != nullptr) {
+        // transposed copy: this thread's 4 rows x 8 columns are 8 runs of 4 consecutive h in the (W, H) plane; the four row blocks
+        // of a warp that share a strip fill whole 32 B sectors
+        in_t* __restrict__ ot = reinterpret_cast<in_t*>(p.out_t) + ((int64_t)b * p.Cout + c) * ((int64_t)p.H * p.W);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            in_t* q = ot + (int64_t)(w0 + i) * p.H + h0;
+            if constexpr (sizeof(in_t) == 2) {
+                uint2 v;
+                v.x = pack2<in_t>(a0[0][i], a0[1][i]);
+                v.y = pack2<in_t>(a0[2][i], a0[3][i]);
+                *reinterpret_cast<uint2*>(q) = v;
+            } else {
+                *reinterpret_cast<float4*>(q) = make_float4(a0[0][i], a0[1][i], a0[2][i], a0[3][i]);
+            }
+        }
+    }
 }
 
 template <typename in_t>
@@ -202,6 +219,10 @@ int dwconv_launch(const DwParams& p, int dtype, cudaStream_t stream) {
         default: set_error("dwconv: unsupported dtype %d", dtype); return VMB_ERR_INVALID;
     }
     VMB_CUDA(cudaGetLastError());
+    if (p.out_t != nullptr) {  // geometries the row-block kernel does not take: the transposed copy as its own pass (same values)
+        VMB_CHECK(p.o_cs == (int64_t)L && p.o_bs == (int64_t)L * p.Cout, "dwconv: the transposed copy needs a dense primary output");
+        return transpose_launch(TransposeParams{p.out, p.out_t, p.B * p.Cout, p.H, p.W}, dtype, stream);
+    }
     return VMB_OK;
 }
 

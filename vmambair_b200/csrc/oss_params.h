@@ -18,6 +18,8 @@ struct DwParams {
     int B, Cout, H, W, mode;
     int64_t x_bs, x_cs, o_bs, o_cs;
     bool vec_ok;  // W % 8 == 0 and 16 B aligned rows: 8-pixel strips
+    void* out_t;  // optional second output: every (H, W) plane transposed to (W, H), dense (B, Cout, W*H) -- the copy of x the
+                  // column-major scan directions read (mode 0 only)
 };
 struct CrossScanParams {
     const void* src[4]; void* out;

@@ -22,6 +22,7 @@ _DTYPES = (torch.float32, torch.bfloat16, torch.float16)
 
 
 _warned = set()
+_DW_T = os.environ.get("VMB_DW_T", "1") == "1"  # depthwise conv writes the transposed copy itself (0: separate vmb_transpose_hw pass)
 
 
 def unsupported_reason(block, x: torch.Tensor):
@@ -121,11 +122,16 @@ def block_forward(block, x: torch.Tensor, out: torch.Tensor = None) -> torch.Ten
     x3 = x.contiguous().view(B, C, L)
     # norm1 + in_conv; SiLU on the z half
     xz = ops.pixlin(x3, c["w_in"], c["b_in"], ln=c["ln1"], act=(C, 2 * C), static_w=True)
-    xc = ops.dwconv3x3(xz[:, :C], c["dw"], c["dw_b"], C, H, W, 0)
-    if L % 8 == 0 and os.environ.get("VMB_FUSED_SCAN", "grouped") == "grouped":
+    grouped = L % 8 == 0 and os.environ.get("VMB_FUSED_SCAN", "grouped") == "grouped"
+    if grouped and _DW_T:
+        xc, xt = ops.dwconv3x3_t(xz[:, :C], c["dw"], c["dw_b"], C, H, W)  # x and its (W,H) copy from one launch
+    else:
+        xc = ops.dwconv3x3(xz[:, :C], c["dw"], c["dw_b"], C, H, W, 0)
+    if grouped:
         # direction-aware scan: directions 0/2 read x and the GEMM on x, 1/3 read the transposed copies; reversed
         # directions walk the same memory backwards -- no gathered / flipped (B,4C,L) operands exist
-        xt = ops.transpose_hw(xc, H, W)
+        if not _DW_T:
+            xt = ops.transpose_hw(xc, H, W)
         d02 = ops.pixlin(xc, c["w_big02"], static_w=True).view(B, 2, C + 2 * N, L)
         d13 = ops.pixlin(xt, c["w_big13"], static_w=True).view(B, 2, C + 2 * N, L)
         src = [(xc, d02[:, 0]), (xt, d13[:, 0]), (xc, d02[:, 1]), (xt, d13[:, 1])]

@@ -197,6 +197,19 @@ def dwconv3x3(x, w9, bias, c_out, H, W, mode, out=None):
     return out
 
 
+def dwconv3x3_t(x, w9, bias, c_out, H, W):
+    """SiLU(dw(x[:c_out])) and its (W,H)-transposed copy from ONE launch -> (out (B,c_out,H*W), out_t (B,c_out,W*H))."""
+    B = x.shape[0]
+    out = torch.empty((B, c_out, H * W), dtype=x.dtype, device=x.device)
+    out_t = torch.empty_like(out)
+    a = _lib.DwconvArgs(_ptr(x), _ptr(w9), _ptr(bias), _ptr(out), B, c_out, H, W, 0,
+                        x.stride(0), x.stride(1), out.stride(0), out.stride(1), _DT[x.dtype])
+    fn = _lib.lib().vmb_dwconv3x3_t
+    with torch.cuda.device(x.device), _timed("dwconv", 0, x.device, 1):
+        _lib.check(fn(C.byref(a), _ptr(out_t), _stream(x)), "vmb_dwconv3x3_t")
+    return out, out_t
+
+
 def cross_scan(srcs, rows, H, W, out=None):
     """srcs: 4 views (B, rows, L) sharing strides -> (B, 4, rows, L) in scan order.  `out`: optional (B, 4, rows, L) view
     (e.g. a channel slice of a wider tensor) with contiguous rows.  The inverse orders are the same call with H and W swapped."""
