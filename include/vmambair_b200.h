@@ -164,6 +164,9 @@ int vmb_transpose_hw(const vmb_transpose_args* a, void* stream);
  * results are bit-identical to torch.nn.functional.pixel_shuffle. */
 typedef struct { const void* x; void* out; int batch, H, W, C; int dtype; } vmb_pixel_shuffle_args;
 int vmb_pixel_shuffle2_nhwc(const vmb_pixel_shuffle_args* a, void* stream);
+/* the same with bias (fp32, 4C values) added to the input channels first: the Upsampler convs (archs/common.py:52) run without
+ * their bias and the permutation pass that follows them adds it -- one elementwise pass over the widest tensors of the net less. */
+int vmb_pixel_shuffle2_nhwc_bias(const vmb_pixel_shuffle_args* a, const float* bias, void* stream);
 
 /* Dense 3x3 convolution, stride 1, zero padding 1 -- the non-OSS convolutions of the U-Net:
  * OverlapPatchEmbed.proj (SRGAN/VmambaIR/archs/MambaSISR6_arch.py:520-528), Downsample.body = Conv2d + PixelUnshuffle(2)

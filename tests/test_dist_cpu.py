@@ -34,14 +34,32 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_flat_allreduce_matches_single_process():
-    world, port = 2, _free_port()
+def _run_world(world):
+    """spawn `world` gloo ranks on a fresh port; a rendezvous that fails (the probed port taken in between, a slow first import under
+    load) is retried on another port"""
     ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
-    [p.start() for p in ps]
-    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
-    [p.join(60) for p in ps]
+    last = None
+    for _ in range(3):
+        port = _free_port()
+        q = ctx.Queue()
+        ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+        [p.start() for p in ps]
+        try:
+            res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda t: t[0])
+            [p.join(60) for p in ps]
+            return res
+        except Exception as e:  # queue.Empty: a rank died or hung before reporting
+            last = e
+            for p in ps:
+                if p.is_alive():
+                    p.terminate()
+                p.join(10)
+    raise last
+
+
+def test_two_rank_flat_allreduce_matches_single_process():
+    world = 2
+    res = _run_world(world)
     assert res[0][3] == (0, 4) and res[1][3] == (4, 8)
     # replicas identical after broadcast, reduced gradients identical on both ranks
     for a, b in zip(res[0][1], res[1][1]):

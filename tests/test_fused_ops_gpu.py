@@ -291,6 +291,11 @@ def test_pixel_shuffle_nhwc_bit_exact(dtype, B, C, H, W):
     ref = F.pixel_shuffle(x, 2)
     assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
     assert torch.equal(out.contiguous(), ref)
+    # with the deferred conv bias: (x + bias) in fp32, rounded once to the storage dtype, then the same permutation
+    bias = torch.randn(4 * C, device="cuda")
+    outb = ops.pixel_shuffle2_nhwc(x.contiguous(memory_format=torch.channels_last), bias)
+    refb = F.pixel_shuffle((x.float() + bias.view(1, -1, 1, 1)).to(dtype), 2)
+    assert torch.equal(outb.contiguous(), refb)
 
 
 def test_sr_tail_channels_last_matches_plain_tail():

@@ -159,3 +159,4 @@ def test_wide_net_dim64_falls_back_per_block_and_runs():
             unet.set_mode("native")
     assert len(blocks) == 8 and torch.isfinite(y).all()
     torch.testing.assert_close(y, ref, rtol=2e-3, atol=2e-4)
+

@@ -188,6 +188,7 @@ SYMBOLS = {
     "vmb_merge_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "vmb_transpose_hw": (C.c_int, [C.POINTER(TransposeArgs), vp]),
     "vmb_pixel_shuffle2_nhwc": (C.c_int, [C.POINTER(PixelShuffleArgs), vp]),
+    "vmb_pixel_shuffle2_nhwc_bias": (C.c_int, [C.POINTER(PixelShuffleArgs), vp, vp]),
     "vmb_conv3x3": (C.c_int, [C.POINTER(Conv3x3Args), vp]),
     "vmb_cross_scan_multi": (C.c_int, [C.POINTER(CrossScanArgs), C.c_int, vp]),
     "vmb_dwconv3x3_t": (C.c_int, [C.POINTER(DwconvArgs), vp, vp]),

@@ -345,6 +345,14 @@ class Upsampler(nn.Sequential):
         super().__init__(*m)
 
 
+_DEFER_TAIL_BIAS = os.environ.get("VMB_TAIL_BIAS", "deferred") == "deferred"
+
+
+def fused_f32(t):
+    from . import fused
+    return fused._f32(t)
+
+
 def ops_mod():
     from . import ops
     return ops
@@ -443,6 +451,7 @@ class MambaSISR6(_MamberUNet):
         wcl = cache[1]
         x = feat.contiguous(memory_format=torch.channels_last)
         mods = list(self.tail[0]) + [self.tail[1]]
+        pending_bias = None
         for i, m in enumerate(mods):
             if inp_img is not None and i == len(mods) - 1 and x.shape[1] % 8 == 0:
                 # conv_last + F.interpolate(inp_img, nearest) + add + NHWC -> NCHW: one kernel of this library (unet.py)
@@ -450,9 +459,16 @@ class MambaSISR6(_MamberUNet):
                 return unet.conv3x3(m, x.contiguous(memory_format=torch.channels_last), ops.CONV_ADD_NEAREST,
                                     add=inp_img.to(x.dtype), add_scale=int(self.scale), nhwc=True)
             if isinstance(m, nn.Conv2d):
-                x = F.conv2d(x, wcl[id(m)], m.bias, m.stride, m.padding)
+                nxt = mods[i + 1] if i + 1 < len(mods) else None
+                # a conv followed by PixelShuffle(2) runs without its bias: the permutation kernel adds it (the library conv would
+                # otherwise spend a separate elementwise pass over its (B,4C,H,W) output on the bias)
+                defer = (m.bias is not None and isinstance(nxt, nn.PixelShuffle) and nxt.upscale_factor == 2 and
+                         m.out_channels % 8 == 0 and _DEFER_TAIL_BIAS)
+                x = F.conv2d(x, wcl[id(m)], None if defer else m.bias, m.stride, m.padding)
+                pending_bias = fused_f32(m.bias) if defer else None
             elif isinstance(m, nn.PixelShuffle) and m.upscale_factor == 2 and x.shape[1] % 8 == 0:
-                x = ops.pixel_shuffle2_nhwc(x.contiguous(memory_format=torch.channels_last))
+                x = ops.pixel_shuffle2_nhwc(x.contiguous(memory_format=torch.channels_last), pending_bias)
+                pending_bias = None
             else:
                 x = m(x)
         if inp_img is not None:

@@ -212,7 +212,16 @@ extern "C" int vmb_pixel_shuffle2_nhwc(const vmb_pixel_shuffle_args* a, void* st
     VMB_CHECK(dt_ok(a->dtype) && a->batch > 0 && a->H > 0 && a->W > 0 && a->C > 0, "pixel_shuffle: bad arguments");
     VMB_CHECK(aligned16(a->x) && (reinterpret_cast<uintptr_t>(a->out) & 3) == 0, "pixel_shuffle: misaligned pointer");
     VMB_CHECK((a->C * elt_size(a->dtype)) % 4 == 0, "pixel_shuffle: output pixels must be whole 32-bit words");
-    PixelShuffleParams p{a->x, a->out, a->batch, a->H, a->W, a->C};
+    PixelShuffleParams p{a->x, a->out, a->batch, a->H, a->W, a->C, nullptr};
+    return pixel_shuffle_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vmb_pixel_shuffle2_nhwc_bias(const vmb_pixel_shuffle_args* a, const float* bias, void* stream) {
+    VMB_CHECK(a && a->x && a->out && bias, "pixel_shuffle_bias: null pointer");
+    VMB_CHECK(dt_ok(a->dtype) && a->batch > 0 && a->H > 0 && a->W > 0 && a->C > 0, "pixel_shuffle_bias: bad arguments");
+    VMB_CHECK(aligned16(a->x) && (reinterpret_cast<uintptr_t>(a->out) & 3) == 0, "pixel_shuffle_bias: misaligned pointer");
+    VMB_CHECK((a->C * elt_size(a->dtype)) % 4 == 0, "pixel_shuffle_bias: output pixels must be whole 32-bit words");
+    PixelShuffleParams p{a->x, a->out, a->batch, a->H, a->W, a->C, bias};
     return pixel_shuffle_launch(p, a->dtype, static_cast<cudaStream_t>(stream));
 }
 

@@ -466,11 +466,8 @@ int launch_generic(const Conv3Params& p, cudaStream_t stream) {
     constexpr int PITCH = 16 * 2 + 16;
     constexpr int SMEM = 2 * (9 * MT * PITCH + kHalo * PITCH);
     auto kern = conv3x3_generic_kernel<T, MT, 16, false>;
-    static bool attr_set = false;  // idempotent: a race only repeats the call
-    if (SMEM > 48 * 1024 && !attr_set) {
-        VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr_set = true;
-    }
+    // per launch, like the scan launchers: the attribute is per device, and a process may drive several (nn.DataParallel-style callers)
+    if (SMEM > 48 * 1024) VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const dim3 grid(cdiv(p.W, kTW) * cdiv(p.H, kTH), cdiv(p.Cout, MT), p.B);
     VMB_CUDA(launch_pdl(kern, grid, dim3(128), SMEM, stream, p));
     return VMB_OK;
@@ -503,11 +500,7 @@ int launch_tma(const Conv3Params& p, int dtype, cudaStream_t stream) {
         if (rc != VMB_OK) return rc;
     }
     auto kern = conv3x3_tma_kernel<T, MT, STAGES, NHWC>;
-    static bool attr_set = false;  // idempotent: a race only repeats the call
-    if (!attr_set) {
-        VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr_set = true;
-    }
+    VMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));  // per device: set at every launch
     const dim3 grid(cdiv(p.W, kTW) * cdiv(p.H, kTH), cdiv(p.Cout, MT), p.B);
     VMB_CUDA(launch_pdl(kern, grid, dim3(128), SMEM, stream, p, mapW, mapX));
     return VMB_OK;

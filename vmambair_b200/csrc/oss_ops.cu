@@ -502,7 +502,20 @@ __global__ void __launch_bounds__(256) pixel_shuffle2_nhwc_kernel(const PixelShu
         const int64_t bh = px / p.W;
         const int h = (int)(bh % p.H);
         const int64_t b = bh / p.H;
-        const uint4 v = __ldg(in + i);
+        uint4 v = __ldg(in + i);
+        if (p.bias != nullptr) {  // the conv in front ran without its bias: input channel 16/sizeof(T) * t + e gets bias[...] here
+            const float* __restrict__ bs = p.bias + t * V;
+            if constexpr (sizeof(T) == 2) {
+                float f[8];
+                unpack8<T>(v, f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += bs[e];
+                v.x = pack2<T>(f[0], f[1]); v.y = pack2<T>(f[2], f[3]); v.z = pack2<T>(f[4], f[5]); v.w = pack2<T>(f[6], f[7]);
+            } else {
+                v.x = __float_as_uint(__uint_as_float(v.x) + bs[0]); v.y = __float_as_uint(__uint_as_float(v.y) + bs[1]);
+                v.z = __float_as_uint(__uint_as_float(v.z) + bs[2]); v.w = __float_as_uint(__uint_as_float(v.w) + bs[3]);
+            }
+        }
         uint32_t wk[4];
         if (sizeof(T) == 2) {
             // halves e0..e7 of the 16 B: element e = (c - 2t) * 4 + k; word_k = {e_k, e_{4+k}}

@@ -47,6 +47,7 @@ struct TransposeParams {
 struct PixelShuffleParams {
     const void* x; void* out;
     int B, H, W, C;  // C = output channels; the input has 4C
+    const float* bias;  // optional fp32 (4C): added to the input channels (the bias of the conv in front)
 };
 struct ChannelParams {
     const float* pooled; float inv_count;

@@ -226,14 +226,20 @@ def cross_scan(srcs, rows, H, W, out=None):
     return out
 
 
-def pixel_shuffle2_nhwc(x):
+def pixel_shuffle2_nhwc(x, bias=None):
     """nn.PixelShuffle(2) on a channels-last tensor: x logical (B,4C,H,W) with NHWC storage -> (B,C,2H,2W), NHWC storage.
-    Bit-identical to F.pixel_shuffle(x, 2)."""
+    Bit-identical to F.pixel_shuffle(x, 2).  bias: optional fp32 (4C), added to x first (the bias of the conv that produced x)."""
     B, C4, H, W = x.shape
     assert C4 % 4 == 0 and x.is_contiguous(memory_format=torch.channels_last)
     out = torch.empty((B, C4 // 4, 2 * H, 2 * W), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
     a = _lib.PixelShuffleArgs(_ptr(x), _ptr(out), B, H, W, C4 // 4, _DT[x.dtype])
-    _run("vmb_pixel_shuffle2_nhwc", a, x, "pixel_shuffle")
+    if bias is None:
+        _run("vmb_pixel_shuffle2_nhwc", a, x, "pixel_shuffle")
+    else:
+        assert bias.dtype == torch.float32 and bias.numel() == C4 and bias.is_contiguous() and bias.device == x.device
+        fn = _lib.lib().vmb_pixel_shuffle2_nhwc_bias
+        with torch.cuda.device(x.device), _timed("pixel_shuffle", 0, x.device, 1):
+            _lib.check(fn(C.byref(a), _ptr(bias), _stream(x)), "vmb_pixel_shuffle2_nhwc_bias")
     return out
 
 
