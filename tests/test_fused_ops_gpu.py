@@ -340,12 +340,14 @@ def test_dwconv_row_block_kernel_bit_identical(dtype, H, W, monkeypatch):
     w = (torch.randn(2 * C, 9, device="cuda") * 0.3).contiguous()
     b = torch.randn(2 * C, device="cuda") * 0.1
     outs = {}
-    for v in ("1", "2"):
+    for v in ("1", "2", "3"):  # 3: the row-block kernel with all row loads issued before the arithmetic
         monkeypatch.setenv("VMB_DW_V", v)
         outs[v] = (ops.dwconv3x3(xin[:, :C], w[:C].contiguous(), b[:C].contiguous(), C, H, W, 0),
-                   ops.dwconv3x3(xin, w, b, C, H, W, 1), ops.dwconv3x3(xin, w, None, C, H, W, 1))
-    for a, r in zip(outs["2"], outs["1"]):
-        assert torch.equal(a, r)
+                   ops.dwconv3x3(xin, w, b, C, H, W, 1), ops.dwconv3x3(xin, w, None, C, H, W, 1),
+                   ops.dwconv3x3(xin, w, None, 2 * C, H, W, 2)) + ops.dwconv3x3_t(xin[:, :C], w[:C].contiguous(), b[:C].contiguous(), C, H, W)
+    for v in ("2", "3"):
+        for a, r in zip(outs[v], outs["1"]):
+            assert torch.equal(a, r)
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
