@@ -127,3 +127,32 @@ def test_pack_conv3x3_weight_layout():
     xp = F.pad(x, (1, 1, 1, 1))
     y = sum(torch.einsum("mk,bkhw->bmhw", wp[3 * ky + kx, :5, :7], xp[:, :, ky:ky + 6, kx:kx + 9]) for ky in range(3) for kx in range(3))
     torch.testing.assert_close(y, F.conv2d(x, w, padding=1), rtol=1e-5, atol=1e-5)
+
+
+def test_conv3x3_store_mode_formulas_match_torch_shuffles():
+    """include/vmambair_b200.h documents the vmb_conv3x3 store modes as index formulas; they must be nn.PixelUnshuffle(2) /
+    nn.PixelShuffle(2) / F.interpolate(..., 'nearest') exactly (the kernels implement the formulas; this pins the formulas)"""
+    import torch.nn.functional as F
+    torch.manual_seed(1)
+    B, M, H, W = 2, 8, 6, 10
+    y = torch.randn(B, M, H, W)
+    un = torch.empty(B, 4 * M, H // 2, W // 2)
+    sh = torch.empty(B, M // 4, 2 * H, 2 * W)
+    for m in range(M):
+        for yy in range(H):
+            for xx in range(W):
+                un[:, 4 * m + 2 * (yy % 2) + xx % 2, yy // 2, xx // 2] = y[:, m, yy, xx]
+                sh[:, m // 4, 2 * yy + (m // 2) % 2, 2 * xx + m % 2] = y[:, m, yy, xx]
+    assert torch.equal(un, F.pixel_unshuffle(y, 2)) and torch.equal(sh, F.pixel_shuffle(y, 2))
+    s = 2
+    add = torch.randn(B, M, H // s, W // s)
+    near = torch.empty(B, M, H, W)
+    for yy in range(H):
+        for xx in range(W):
+            near[:, :, yy, xx] = add[:, :, yy // s, xx // s]
+    assert torch.equal(near, F.interpolate(add, scale_factor=s, mode="nearest"))
+    # cross-scan orders documented for vmb_cross_scan(_multi): pi_1(w*H + h) = h*W + w and the reversed orders
+    Hh, Ww = 3, 5
+    img = torch.arange(Hh * Ww).view(Hh, Ww)
+    col_major = torch.tensor([img[h, w] for w in range(Ww) for h in range(Hh)])
+    assert torch.equal(col_major, img.t().contiguous().view(-1))
